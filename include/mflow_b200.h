@@ -1,0 +1,175 @@
+/*
+ * mflow_b200.h - C ABI of libmflow_b200.so: the B200 (sm_100a) kernels behind the
+ * manifold-flow neural-spline coupling hot path.
+ *
+ * The reference (johannbrehmer/manifold-flow) has no FFI: its boundary is the Python
+ * class API of the `manifold_flow` package.  The drop-in `manifold_flow` package in
+ * manifold-flow_b200/ keeps that API and calls the entry points below through ctypes
+ * (manifold_flow/b200/cabi.py).  Each entry point names the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 (or int32/int64 where stated) unless it is a
+ *    `const mflow_*_desc*`, which is a HOST pointer read before the launch;
+ *  - nothing allocates, synchronises or touches the default stream: the caller provides
+ *    outputs and workspaces and a `cudaStream_t` (passed as void*), so every call is
+ *    CUDA-graph capturable;
+ *  - return value 0 = launched; non-zero = MFLOW_E_* and mflow_last_error_string() explains;
+ *  - no C++ types, no torch types, no exceptions cross this boundary.
+ */
+#ifndef MFLOW_B200_H
+#define MFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFLOW_ABI_VERSION 1
+#if defined(__GNUC__)
+#define MFLOW_API __attribute__((visibility("default")))
+#else
+#define MFLOW_API
+#endif
+
+enum {
+  MFLOW_OK = 0,
+  MFLOW_E_BADARG = 1,   /* unsupported shape / null pointer / misaligned */
+  MFLOW_E_LAUNCH = 2,   /* cudaGetLastError() after the launch           */
+  MFLOW_E_NODEVICE = 3, /* no sm_100 device visible                       */
+  MFLOW_E_WORKSPACE = 4 /* workspace too small                            */
+};
+
+MFLOW_API int mflow_version(void);
+MFLOW_API const char* mflow_last_error_string(void);
+/* 0 if a CUDA device with compute capability 10.x is current, else MFLOW_E_NODEVICE. */
+MFLOW_API int mflow_check_device(void);
+
+/* ------------------------------------------------------------------------------------
+ * (a) Rational-quadratic spline with linear tails.
+ * Replaces manifold_flow/transforms/splines/rational_quadratic.py:16-168
+ * (unconstrained_rational_quadratic_spline + rational_quadratic_spline), the bin search
+ * manifold_flow/utils/various.py:472-474, the parameter slicing / pre-scale of
+ * manifold_flow/transforms/coupling.py:501-511, the per-sample reduction :279 and the
+ * split / merge of CouplingTransform.forward/inverse :58-185.
+ *
+ * Elements are indexed (o, c, i): o = outer index (sample for images, sample for vectors),
+ * c = transformed channel / feature, i = inner contiguous index (pixel; 1 for vectors).
+ *   x  element  at x  + o*x_so + c*x_sc + i
+ *   y  element  at y  + o*y_so + c*y_sc + i
+ *   parameter p (0 <= p < 3K-1: K widths, K heights, K-1 derivatives) of the element at
+ *              params + o*p_so + c*p_sc + p*p_sp + i*p_si
+ * Two layouts are implemented:
+ *   "planes" (image, conditioner output [B, C_t*P, H, W]): p_si == 1, p_sp == n_inner
+ *   "rows"   (vector, conditioner output [B, C_t*P]):       n_inner == 1, p_sp == 1
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_outer;  /* O */
+  int64_t n_chan;   /* C_t */
+  int64_t n_inner;  /* I */
+  int64_t x_so, x_sc;
+  int64_t y_so, y_sc;
+  int64_t p_so, p_sc, p_sp, p_si;
+  int32_t num_bins; /* K in {2..16} */
+  int32_t inverse;  /* 0 forward, 1 inverse */
+  float tail_bound; /* T: spline on [-T, T]^2, identity outside (closed interval) */
+  float min_bin_width, min_bin_height, min_derivative;
+  float wh_divisor; /* widths/heights logits are divided by this (sqrt(hidden)); 1 = off */
+  /* identity part copied through by the same launch (coupling merge); n_id_chan == 0 = off.
+   *   src at x + o*x_so + id_off + c*id_sc + i,  dst at y + o*y_so + id_off + c*id_sc + i */
+  int64_t n_id_chan, id_off, id_sc;
+} mflow_rqs_desc;
+
+/* Forward or inverse evaluation.
+ *   lad_elem   : optional [O*C_t*I] per-element logabsdet, same indexing as a dense (o,c,i) array
+ *   lad_sample : optional [O]; receives lad_base[o] (or 0 when lad_base is NULL) + sum over (c,i)
+ *   bins       : optional int32 [O*C_t*I] bin index per element (-1 in the tails)
+ *   workspace  : device scratch of mflow_rqs_workspace_bytes(desc) bytes: 256 KiB of per-sample
+ *                arrival counters (must be zero on first use; every launch leaves them zeroed)
+ *                followed by per-CTA partial sums.  One workspace per stream. */
+MFLOW_API int64_t mflow_rqs_workspace_bytes(const mflow_rqs_desc* desc);
+MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* desc, const float* x, const float* params, float* y,
+                    float* lad_elem, float* lad_sample, const float* lad_base, int32_t* bins,
+                    void* workspace, void* stream);
+
+/* Backward of mflow_rqs_apply.
+ *   x_in       : the tensor that was the INPUT of the apply call
+ *   x_out      : its OUTPUT (only read when desc->inverse; may be NULL otherwise)
+ *   g_out      : gradient w.r.t. the output tensor (same indexing as y), may be NULL (= 0)
+ *   g_lad_sample / g_lad_elem : gradient w.r.t. lad_sample [O] / lad_elem (either may be NULL)
+ *   g_in       : gradient w.r.t. the input tensor (transform part and, if n_id_chan, identity part)
+ *   g_params   : gradient w.r.t. params, same indexing as params; every entry is written */
+MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* desc, const float* x_in, const float* x_out,
+                       const float* params, const float* g_out, const float* g_lad_sample,
+                       const float* g_lad_elem, float* g_in, float* g_params, void* stream);
+
+/* Test entry: the kernel's own bin search on caller-provided knots (bit-exactness pin,
+ * utils/various.py:472-474).  knots [n, K+1] row-major, values [n] -> bins int32 [n]. */
+MFLOW_API int mflow_rqs_search(const float* knots, const float* values, int32_t* bins, int64_t n,
+                     int32_t num_bins, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) Linear glue.
+ * ---------------------------------------------------------------------------------- */
+/* y[o, :, i] = M x[o, :, i] + m  for a dense C x C matrix (C <= 128): the fused form of
+ * ActNorm (transforms/normalization.py:99-131), the channel permutation and LU map of
+ * OneByOneConvolution (transforms/conv.py:16-55, transforms/lu.py:56-95) and, for vectors,
+ * RandomPermutation + LULinear (architectures/vector_transforms.py:39-46).
+ *   element (o, c, i) at ptr + o*so + c*sc + i*si;  M row-major [C, C] (y_c = sum_k M[c,k] x_k). */
+typedef struct {
+  int64_t n_outer, n_chan, n_inner;
+  int64_t x_so, x_sc, x_si;
+  int64_t y_so, y_sc, y_si;
+} mflow_mix_desc;
+MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* desc, const float* x, const float* mat, const float* bias,
+                        float* y, void* stream);
+/* Weight gradients of the above: g_mat[c,k] = sum_{o,i} g_y[o,c,i] x[o,k,i], g_bias[c] = sum g_y.
+ * workspace: device scratch of mflow_chanmix_wgrad_workspace_bytes(desc) bytes; its first 16 bytes hold
+ * an arrival counter that must be zero on first use (left zeroed by every launch). */
+MFLOW_API int64_t mflow_chanmix_wgrad_workspace_bytes(const mflow_mix_desc* desc);
+MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* desc, const float* x, const float* g_y, float* g_mat,
+                        float* g_bias, void* workspace, void* stream);
+
+/* 2x2 space-to-depth with a fused scalar affine map: y = squeeze(x) * scale + shift (forward) or
+ * y = unsqueeze((x - shift) / scale) (inverse).  SqueezeTransform (transforms/reshape.py:29-57) and
+ * AffineScalarTransform (transforms/standard.py:41-57).  x [B, C, H, W] contiguous. */
+MFLOW_API int mflow_squeeze2x2(const float* x, float* y, int64_t batch, int64_t chan, int64_t height, int64_t width,
+                     int32_t inverse, float scale, float shift, void* stream);
+
+/* y = x * scale + shift (forward) / (x - shift) / scale (inverse) over n floats:
+ * AffineScalarTransform (transforms/standard.py:41-57). */
+MFLOW_API int mflow_affine_scalar(const float* x, float* y, int64_t n, float scale, float shift, int32_t inverse,
+                        void* stream);
+
+/* y[o, j] = x[o, perm[j]] over rows of length n: Permutation._permute (transforms/permutations.py:73). */
+MFLOW_API int mflow_permute_rows(const float* x, const int64_t* perm, float* y, int64_t rows, int64_t n, void* stream);
+
+/* LogTanh (transforms/nonlinearities.py:38-95) on [rows, n]; lad_sample[o] = sum_j logabsdet. */
+MFLOW_API int mflow_logtanh_apply(const float* x, float* y, float* lad_sample, int64_t rows, int64_t n, int32_t inverse,
+                        float cut_point, void* stream);
+MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const float* g_lad_sample, float* g_x,
+                           int64_t rows, int64_t n, int32_t inverse, float cut_point, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Likelihood epilogues.
+ * ---------------------------------------------------------------------------------- */
+/* log_prob[o] = logN(u[o,:]; 0, 1) + logN(clamp(v[o,:], +-clip); 0, eps^2) + sum of the addends.
+ * StandardNormal / RescaledNormal (distributions/normal.py:18-23, 52-59) and
+ * ManifoldFlow._log_prob "pie"/"mf-fixed-manifold" (flows/manifold_flow.py:125-128,149-152).
+ * v may be NULL (n_v = 0); clip <= 0 disables clipping; add0/add1 optional [O]. */
+MFLOW_API int mflow_gauss_logprob(const float* u, int64_t n_u, int64_t u_stride, const float* v, int64_t n_v,
+                        int64_t v_stride, float eps, float clip, const float* add0, const float* add1,
+                        float* log_prob, int64_t rows, void* stream);
+MFLOW_API int mflow_gauss_logprob_backward(const float* u, int64_t n_u, int64_t u_stride, const float* v, int64_t n_v,
+                                 int64_t v_stride, float eps, float clip, const float* g_log_prob,
+                                 float* g_u, float* g_v, int64_t rows, void* stream);
+
+/* (d) logdet[o] = log det (J_o^T J_o) for J [O, D, n] row-major, n <= 32, by Cholesky of the Gram
+ * matrix: ManifoldFlow._log_prob "mf" (flows/manifold_flow.py:140-147: bmm + slogdet). */
+MFLOW_API int mflow_jtj_logdet(const float* jac, float* logdet, int64_t rows, int32_t d, int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFLOW_B200_H */

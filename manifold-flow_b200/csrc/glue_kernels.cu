@@ -1,0 +1,486 @@
+// Linear-glue and likelihood-epilogue kernels (kernels (c) and (d) of BASELINE.json:north_star).
+// All of them are HBM-bound copies / reductions; the point is to do each in ONE coalesced pass
+// where the reference issues several ATen launches with intermediate tensors.
+#include <math.h>
+#include <stdarg.h>
+
+#include "mflow_common.cuh"
+
+namespace mflow {
+
+// ---------------------------------------------------------------------------------------------
+// y[o, :, i] = M x[o, :, i] + m          (ActNorm + channel permutation + LU 1x1 conv, fused)
+// reference: transforms/normalization.py:99-131, transforms/conv.py:16-55, transforms/lu.py:56-95
+// A CTA owns 32 consecutive "pixels" q = o*I + i; 4 warps split the output channels; M sits in
+// shared memory and is read as a broadcast, the x tile is read with lane == pixel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMixPix = 32;
+constexpr int kMixThreads = 128;
+
+__global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __restrict__ x, const float* __restrict__ mat,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              int64_t n_pix, int C, int64_t I, int64_t x_so, int64_t x_sc,
+                                                              int64_t x_si, int64_t y_so, int64_t y_sc, int64_t y_si) {
+  extern __shared__ float smem[];
+  float* s_mat = smem;                 // [C][C]
+  float* s_x = smem + C * C;           // [C][33]
+  float* s_b = s_x + C * (kMixPix + 1);  // [C]
+  for (int idx = threadIdx.x; idx < C * C; idx += kMixThreads) s_mat[idx] = mat[idx];
+  for (int idx = threadIdx.x; idx < C; idx += kMixThreads) s_b[idx] = bias ? bias[idx] : 0.f;
+  const int64_t q0 = (int64_t)blockIdx.x * kMixPix;
+  const int n_here = (int)min((int64_t)kMixPix, n_pix - q0);
+  const bool chan_fast = (x_sc == 1);  // rows layout: channels contiguous -> walk channels fastest
+  for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixThreads) {
+    int k, pq;
+    if (chan_fast) { pq = idx / C; k = idx - pq * C; } else { k = idx / kMixPix; pq = idx - k * kMixPix; }
+    float v = 0.f;
+    if (pq < n_here) {
+      const int64_t q = q0 + pq, o = q / I, i = q - o * I;
+      v = x[o * x_so + k * x_sc + i * x_si];
+    }
+    s_x[k * (kMixPix + 1) + pq] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (y_sc == 1) {
+    // rows layout: transpose through shared memory so that stores are contiguous
+    __shared__ float s_y[kMixPix][33];
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      for (int cc = warp; cc < 32 && c0 + cc < C; cc += 4) {
+        const int c = c0 + cc;
+        float acc = s_b[c];
+        for (int k = 0; k < C; ++k) acc = fmaf(s_mat[c * C + k], s_x[k * (kMixPix + 1) + lane], acc);
+        s_y[lane][cc] = acc;
+      }
+      __syncthreads();
+      const int nc = min(32, C - c0);
+      for (int idx = threadIdx.x; idx < kMixPix * nc; idx += kMixThreads) {
+        const int pq = idx / nc, cc = idx - pq * nc;
+        if (pq < n_here) {
+          const int64_t q = q0 + pq, o = q / I, i = q - o * I;
+          y[o * y_so + (c0 + cc) * y_sc + i * y_si] = s_y[pq][cc];
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  if (lane < n_here) {
+    const int64_t q = q0 + lane, o = q / I, i = q - o * I;
+    for (int c = warp; c < C; c += 4) {
+      float acc = s_b[c];
+      for (int k = 0; k < C; ++k) acc = fmaf(s_mat[c * C + k], s_x[k * (kMixPix + 1) + lane], acc);
+      y[o * y_so + c * y_sc + i * y_si] = acc;
+    }
+  }
+}
+
+// g_mat[c,k] = sum_q g_y[c,q] x[k,q],  g_bias[c] = sum_q g_y[c,q]: each CTA accumulates a slab of
+// pixels into shared memory, writes its partial [C*C + C] block; the last-arriving CTA reduces the
+// partials in a fixed order (deterministic).
+__global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                    float* __restrict__ g_mat, float* __restrict__ g_bias,
+                                                                    float* __restrict__ partial, unsigned int* counter,
+                                                                    int64_t n_pix, int C, int64_t I, int64_t x_so, int64_t x_sc,
+                                                                    int64_t x_si, int64_t y_so, int64_t y_sc, int64_t y_si) {
+  extern __shared__ float smem[];
+  const int pitch = kMixPix + 1;
+  float* s_acc = smem;                  // [C*C + C]
+  float* s_x = s_acc + C * C + C;       // [C][33]
+  float* s_g = s_x + C * pitch;         // [C][33]
+  __shared__ int s_last;
+  const int n_out = C * C + C;
+  for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) s_acc[idx] = 0.f;
+  const bool chan_fast = (x_sc == 1);
+  const int64_t n_tiles = (n_pix + kMixPix - 1) / kMixPix;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t q0 = tile * kMixPix;
+    const int n_here = (int)min((int64_t)kMixPix, n_pix - q0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixThreads) {
+      int k, pq;
+      if (chan_fast) { pq = idx / C; k = idx - pq * C; } else { k = idx / kMixPix; pq = idx - k * kMixPix; }
+      float vx = 0.f, vg = 0.f;
+      if (pq < n_here) {
+        const int64_t q = q0 + pq, o = q / I, i = q - o * I;
+        vx = x[o * x_so + k * x_sc + i * x_si];
+        vg = gy[o * y_so + k * y_sc + i * y_si];
+      }
+      s_x[k * pitch + pq] = vx;
+      s_g[k * pitch + pq] = vg;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) {
+      float acc = 0.f;
+      if (idx < C * C) {
+        const int c = idx / C, k = idx - c * C;
+#pragma unroll 8
+        for (int pq = 0; pq < kMixPix; ++pq) acc = fmaf(s_g[c * pitch + pq], s_x[k * pitch + pq], acc);
+      } else {
+        const int c = idx - C * C;
+#pragma unroll 8
+        for (int pq = 0; pq < kMixPix; ++pq) acc += s_g[c * pitch + pq];
+      }
+      s_acc[idx] += acc;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) partial[(int64_t)blockIdx.x * n_out + idx] = s_acc[idx];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) {
+    float acc = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (int64_t)b * n_out + idx);
+    if (idx < C * C) g_mat[idx] = acc; else if (g_bias) g_bias[idx - C * C] = acc;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2 space-to-depth + scalar affine      transforms/reshape.py:29-57, transforms/standard.py:41-57
+// ---------------------------------------------------------------------------------------------
+__global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int C, int H, int W,
+                               int inverse, float scale, float shift) {
+  // H, W are the LARGE (unsqueezed) spatial sizes; squeezed tensor is [B, 4C, H/2, W/2]
+  const int H2 = H >> 1, W2 = W >> 1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    if (!inverse) {  // idx enumerates the squeezed output (coalesced stores)
+      int64_t r = idx;
+      const int w2 = r % W2; r /= W2;
+      const int h2 = r % H2; r /= H2;
+      const int c4 = r % (4 * C); const int64_t b = r / (4 * C);
+      const int c = c4 >> 2, fh = (c4 >> 1) & 1, fw = c4 & 1;
+      const float v = x[((b * C + c) * H + (2 * h2 + fh)) * W + (2 * w2 + fw)];
+      y[idx] = __fadd_rn(__fmul_rn(v, scale), shift);
+    } else {  // idx enumerates the unsqueezed output
+      int64_t r = idx;
+      const int w = r % W; r /= W;
+      const int h = r % H; r /= H;
+      const int c = r % C; const int64_t b = r / C;
+      const int c4 = c * 4 + (h & 1) * 2 + (w & 1);
+      const float v = x[((b * 4 * C + c4) * H2 + (h >> 1)) * W2 + (w >> 1)];
+      y[idx] = (scale == 1.f && shift == 0.f) ? v : __fdiv_rn(__fsub_rn(v, shift), scale);
+    }
+  }
+}
+
+// AffineScalarTransform alone (transforms/standard.py:41-57): mul-then-add / sub-then-div, like ATen
+__global__ void affine_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float scale, float shift,
+                                     int inverse) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[idx];
+    y[idx] = inverse ? __fdiv_rn(__fsub_rn(v, shift), scale) : __fadd_rn(__fmul_rn(v, scale), shift);
+  }
+}
+
+__global__ void permute_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ perm, float* __restrict__ y,
+                                    int64_t rows, int64_t n) {
+  const int64_t total = rows * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = idx / n, j = idx - o * n;
+    y[idx] = x[o * n + perm[j]];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LogTanh                                   transforms/nonlinearities.py:38-95
+// ---------------------------------------------------------------------------------------------
+struct LogTanhConsts {
+  float cut, inv_cut, alpha, beta, log_ab;
+};
+
+__device__ __forceinline__ void logtanh_eval(float v, const LogTanhConsts& c, int inverse, float& out, float& lad) {
+  if (!inverse) {
+    if (v > c.cut) { out = c.alpha * logf(c.beta * v); lad = logf(c.alpha / v); }
+    else if (v < -c.cut) { out = c.alpha * -logf(-c.beta * v); lad = logf(-c.alpha / v); }
+    else { out = tanhf(v); lad = logf(1.f - out * out); }
+  } else {
+    if (v > c.inv_cut) { out = expf(v / c.alpha) / c.beta; lad = -c.log_ab + v / c.alpha; }
+    else if (v < -c.inv_cut) { out = -expf(-v / c.alpha) / c.beta; lad = -c.log_ab - v / c.alpha; }
+    else { out = 0.5f * logf((1.f + v) / (1.f - v)); lad = -logf(1.f - v * v); }
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) logtanh_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                      const float* __restrict__ gl, float* __restrict__ y,
+                                                      float* __restrict__ lad_sample, int64_t n, int inverse,
+                                                      LogTanhConsts c) {
+  __shared__ float red[8];
+  const int64_t o = blockIdx.x;
+  const float* xo = x + o * n;
+  float acc = 0.f;
+  const float g_l = BWD ? (gl ? gl[o] : 0.f) : 0.f;
+  for (int64_t j = threadIdx.x; j < n; j += 256) {
+    const float v = xo[j];
+    if (!BWD) {
+      float out, lad;
+      logtanh_eval(v, c, inverse, out, lad);
+      y[o * n + j] = out;
+      acc += lad;
+    } else {
+      // d out / d v and d lad / d v
+      float dy, dl;
+      if (!inverse) {
+        if (v > c.cut || v < -c.cut) { dy = c.alpha / fabsf(v); dl = -1.f / v; }
+        else { const float t = tanhf(v); dy = 1.f - t * t; dl = -2.f * t; }
+      } else {
+        if (v > c.inv_cut) { dy = expf(v / c.alpha) / (c.alpha * c.beta); dl = 1.f / c.alpha; }
+        else if (v < -c.inv_cut) { dy = expf(-v / c.alpha) / (c.alpha * c.beta); dl = -1.f / c.alpha; }
+        else { dy = 1.f / (1.f - v * v); dl = 2.f * v / (1.f - v * v); }
+      }
+      y[o * n + j] = (gy ? gy[o * n + j] : 0.f) * dy + g_l * dl;
+    }
+  }
+  if (!BWD && lad_sample) {
+    const float s = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) lad_sample[o] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian log-likelihood epilogue  distributions/normal.py:18-23,52-59; flows/manifold_flow.py:125-128
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gauss_logprob_kernel(const float* __restrict__ u, int64_t n_u, int64_t u_stride,
+                                                            const float* __restrict__ v, int64_t n_v, int64_t v_stride,
+                                                            float inv_eps2, float clip, float log_z_u, float log_z_v,
+                                                            const float* __restrict__ add0, const float* __restrict__ add1,
+                                                            float* __restrict__ out) {
+  __shared__ float red[8];
+  const int64_t o = blockIdx.x;
+  float su = 0.f, sv = 0.f;
+  for (int64_t j = threadIdx.x; j < n_u; j += 256) { const float t = u[o * u_stride + j]; su = fmaf(t, t, su); }
+  for (int64_t j = threadIdx.x; j < n_v; j += 256) {
+    float t = v[o * v_stride + j];
+    if (clip > 0.f) t = fminf(fmaxf(t, -clip), clip);
+    sv = fmaf(t, t, sv);
+  }
+  su = block_sum<256>(su, red);
+  sv = block_sum<256>(sv, red);
+  if (threadIdx.x == 0) {
+    float lp = -0.5f * su - log_z_u;
+    if (n_v > 0) lp = lp + (-0.5f * sv * inv_eps2 - log_z_v);
+    if (add0) lp = lp + add0[o];
+    if (add1) lp = lp + add1[o];
+    out[o] = lp;
+  }
+}
+
+__global__ void gauss_logprob_bwd_kernel(const float* __restrict__ u, int64_t n_u, int64_t u_stride,
+                                         const float* __restrict__ v, int64_t n_v, int64_t v_stride, float inv_eps2,
+                                         float clip, const float* __restrict__ g, float* __restrict__ g_u,
+                                         float* __restrict__ g_v, int64_t rows) {
+  const int64_t n = n_u + n_v, total = rows * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = idx / n, j = idx - o * n;
+    const float go = g[o];
+    if (j < n_u) {
+      if (g_u) g_u[o * n_u + j] = -u[o * u_stride + j] * go;
+    } else if (g_v) {
+      const float t = v[o * v_stride + (j - n_u)];
+      const bool clipped = clip > 0.f && (t < -clip || t > clip);
+      g_v[o * n_v + (j - n_u)] = clipped ? 0.f : -t * inv_eps2 * go;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (d) log det(J^T J) per sample, J [D, n], n <= 32: one warp per sample.  The Gram matrix is
+// accumulated and factorised (LDL^T, no pivoting: it is symmetric positive definite) in fp64 so that
+// ill-conditioned Jacobians keep their digits.      flows/manifold_flow.py:140-147
+// ---------------------------------------------------------------------------------------------
+constexpr int kJtjWarps = 4;
+__global__ void __launch_bounds__(kJtjWarps * 32) jtj_logdet_kernel(const float* __restrict__ jac, float* __restrict__ out,
+                                                                   int64_t rows, int D, int n) {
+  __shared__ double s_g[kJtjWarps][32 * 33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t o = (int64_t)blockIdx.x * kJtjWarps + warp;
+  if (o >= rows) return;
+  double* g = s_g[warp];
+  const float* J = jac + o * (int64_t)D * n;
+  // lane owns column `lane` of the Gram matrix: g[a][lane] = sum_d J[d][a] J[d][lane]
+  for (int a = 0; a < n; ++a) {
+    double acc = 0.0;
+    if (lane < n)
+      for (int d = 0; d < D; ++d) acc += (double)J[d * n + a] * (double)J[d * n + lane];
+    g[a * 33 + lane] = acc;
+  }
+  __syncwarp();
+  double logdet = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const double piv = g[k * 33 + k];
+    logdet += log(fabs(piv));
+    // rank-1 update of the trailing block: lane owns column `lane`
+    if (lane > k && lane < n) {
+      const double f = g[k * 33 + lane] / piv;
+      for (int r = k + 1; r < n; ++r) g[r * 33 + lane] -= g[r * 33 + k] * f;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) out[o] = (float)logdet;
+}
+
+static unsigned grid_for(int64_t total, int threads) {
+  int64_t g = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static size_t mix_smem(int C) { return (size_t)(C * C + C * (kMixPix + 1) + C) * sizeof(float); }
+static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
+static int wgrad_grid(int64_t n_pix) {
+  int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
+  return (int)(tiles < 1 ? 1 : (tiles > kNumSMs ? kNumSMs : tiles));
+}
+
+}  // namespace mflow
+
+using namespace mflow;
+
+extern "C" MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* d, const float* x, const float* mat, const float* bias, float* y,
+                                   void* stream) {
+  MFLOW_REQUIRE(d && x && mat && y, "null pointer");
+  MFLOW_REQUIRE(d->n_chan >= 1 && d->n_chan <= 128, "chanmix supports 1..128 channels, got %lld", (long long)d->n_chan);
+  const int64_t n_pix = d->n_outer * d->n_inner;
+  if (n_pix == 0) return MFLOW_OK;
+  const int C = (int)d->n_chan;
+  const size_t smem = mix_smem(C);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const unsigned grid = (unsigned)((n_pix + kMixPix - 1) / kMixPix);
+  chanmix_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, mat, bias, y, n_pix, C, d->n_inner, d->x_so, d->x_sc,
+                                                                      d->x_si, d->y_so, d->y_sc, d->y_si);
+  return check_launch("chanmix_kernel");
+}
+
+extern "C" MFLOW_API int64_t mflow_chanmix_wgrad_workspace_bytes(const mflow_mix_desc* d) {
+  if (!d) return 0;
+  const int64_t n_out = d->n_chan * d->n_chan + d->n_chan;
+  return 16 + (int64_t)wgrad_grid(d->n_outer * d->n_inner) * n_out * 4;
+}
+
+extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const float* x, const float* g_y, float* g_mat, float* g_bias,
+                                   void* workspace, void* stream) {
+  MFLOW_REQUIRE(d && x && g_y && g_mat && workspace, "null pointer");
+  MFLOW_REQUIRE(d->n_chan >= 1 && d->n_chan <= 96, "chanmix_wgrad supports 1..96 channels, got %lld", (long long)d->n_chan);
+  const int64_t n_pix = d->n_outer * d->n_inner;
+  const int C = (int)d->n_chan;
+  const int grid = wgrad_grid(n_pix);
+  const int64_t n_out = (int64_t)C * C + C;
+  // arrival counter in the first 16 bytes (zero between launches), partial blocks after it
+  unsigned int* counter = (unsigned int*)workspace;
+  float* partial = (float*)((char*)workspace + 16);
+  (void)n_out;
+  const size_t smem = wgrad_smem(C);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  chanmix_wgrad_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, g_y, g_mat, g_bias, partial, counter,
+                                                                            n_pix, C, d->n_inner, d->x_so, d->x_sc, d->x_si,
+                                                                            d->y_so, d->y_sc, d->y_si);
+  return check_launch("chanmix_wgrad_kernel");
+}
+
+extern "C" MFLOW_API int mflow_squeeze2x2(const float* x, float* y, int64_t batch, int64_t chan, int64_t height, int64_t width,
+                                int32_t inverse, float scale, float shift, void* stream) {
+  MFLOW_REQUIRE(x && y, "null pointer");
+  // forward: x is [B, C, H, W]; inverse: x is [B, 4C', H', W'] and chan/height/width describe x as given
+  int64_t C, H, W;
+  if (!inverse) {
+    MFLOW_REQUIRE(height % 2 == 0 && width % 2 == 0, "Input image size not compatible with the factor.");
+    C = chan; H = height; W = width;
+  } else {
+    MFLOW_REQUIRE(chan >= 4 && chan % 4 == 0, "Invalid number of channel dimensions.");
+    C = chan / 4; H = height * 2; W = width * 2;
+  }
+  MFLOW_REQUIRE(scale != 0.f, "Scale cannot be zero.");
+  const int64_t total = batch * C * H * W;
+  if (total == 0) return MFLOW_OK;
+  squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, (int)C, (int)H, (int)W, inverse, scale,
+                                                                          shift);
+  return check_launch("squeeze_kernel");
+}
+
+extern "C" MFLOW_API int mflow_affine_scalar(const float* x, float* y, int64_t n, float scale, float shift, int32_t inverse,
+                                             void* stream) {
+  MFLOW_REQUIRE(x && y, "null pointer");
+  MFLOW_REQUIRE(scale != 0.f, "Scale cannot be zero.");
+  if (n == 0) return MFLOW_OK;
+  affine_scalar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, scale, shift, inverse);
+  return check_launch("affine_scalar_kernel");
+}
+
+extern "C" MFLOW_API int mflow_permute_rows(const float* x, const int64_t* perm, float* y, int64_t rows, int64_t n, void* stream) {
+  MFLOW_REQUIRE(x && perm && y, "null pointer");
+  if (rows * n == 0) return MFLOW_OK;
+  permute_rows_kernel<<<grid_for(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(x, perm, y, rows, n);
+  return check_launch("permute_rows_kernel");
+}
+
+static LogTanhConsts logtanh_consts(float cut_point) {
+  // transforms/nonlinearities.py:49-53 (float64 on the host)
+  const double cut = cut_point;
+  const double inv_cut = tanh(cut);
+  const double alpha = (1.0 - tanh(tanh(cut))) / cut;
+  const double beta = exp((tanh(cut) - alpha * log(cut)) / alpha);
+  LogTanhConsts c;
+  c.cut = (float)cut; c.inv_cut = (float)inv_cut; c.alpha = (float)alpha; c.beta = (float)beta;
+  c.log_ab = (float)log(alpha * beta);
+  return c;
+}
+
+extern "C" MFLOW_API int mflow_logtanh_apply(const float* x, float* y, float* lad_sample, int64_t rows, int64_t n, int32_t inverse,
+                                   float cut_point, void* stream) {
+  MFLOW_REQUIRE(x && y, "null pointer");
+  MFLOW_REQUIRE(cut_point > 0.f, "Cut point must be positive.");
+  if (rows == 0) return MFLOW_OK;
+  logtanh_kernel<false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, y, lad_sample, n, inverse,
+                                                                           logtanh_consts(cut_point));
+  return check_launch("logtanh_kernel");
+}
+
+extern "C" MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const float* g_lad_sample, float* g_x, int64_t rows,
+                                      int64_t n, int32_t inverse, float cut_point, void* stream) {
+  MFLOW_REQUIRE(x && g_x, "null pointer");
+  if (rows == 0) return MFLOW_OK;
+  logtanh_kernel<true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, g_y, g_lad_sample, g_x, nullptr, n, inverse,
+                                                                          logtanh_consts(cut_point));
+  return check_launch("logtanh_kernel(bwd)");
+}
+
+extern "C" MFLOW_API int mflow_gauss_logprob(const float* u, int64_t n_u, int64_t u_stride, const float* v, int64_t n_v,
+                                   int64_t v_stride, float eps, float clip, const float* add0, const float* add1,
+                                   float* log_prob, int64_t rows, void* stream) {
+  MFLOW_REQUIRE((u || n_u == 0) && log_prob, "null pointer");
+  MFLOW_REQUIRE(n_v == 0 || (v != nullptr && eps > 0.f), "orthogonal part needs a pointer and eps > 0");
+  if (rows == 0) return MFLOW_OK;
+  const double two_pi = 6.283185307179586;
+  const float log_z_u = (float)(0.5 * (double)n_u * log(two_pi));
+  const float log_z_v = n_v ? (float)(0.5 * (double)n_v * log(two_pi) + (double)n_v * log((double)eps)) : 0.f;
+  const float inv_eps2 = n_v ? (float)(1.0 / ((double)eps * (double)eps)) : 0.f;
+  gauss_logprob_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(u, n_u, u_stride, v, n_v, v_stride, inv_eps2, clip,
+                                                                          log_z_u, log_z_v, add0, add1, log_prob);
+  return check_launch("gauss_logprob_kernel");
+}
+
+extern "C" MFLOW_API int mflow_gauss_logprob_backward(const float* u, int64_t n_u, int64_t u_stride, const float* v, int64_t n_v,
+                                            int64_t v_stride, float eps, float clip, const float* g_log_prob, float* g_u,
+                                            float* g_v, int64_t rows, void* stream) {
+  MFLOW_REQUIRE((u || n_u == 0) && g_log_prob, "null pointer");
+  if (rows == 0) return MFLOW_OK;
+  const float inv_eps2 = n_v ? (float)(1.0 / ((double)eps * (double)eps)) : 0.f;
+  gauss_logprob_bwd_kernel<<<grid_for(rows * (n_u + n_v), 256), 256, 0, (cudaStream_t)stream>>>(
+      u, n_u, u_stride, v, n_v, v_stride, inv_eps2, clip, g_log_prob, g_u, g_v, rows);
+  return check_launch("gauss_logprob_bwd_kernel");
+}
+
+extern "C" MFLOW_API int mflow_jtj_logdet(const float* jac, float* logdet, int64_t rows, int32_t d, int32_t n, void* stream) {
+  MFLOW_REQUIRE(jac && logdet, "null pointer");
+  MFLOW_REQUIRE(n >= 1 && n <= 32, "jtj_logdet supports latent dimension 1..32, got %d", (int)n);
+  MFLOW_REQUIRE(d >= n, "J must have at least as many rows as columns");
+  if (rows == 0) return MFLOW_OK;
+  jtj_logdet_kernel<<<(unsigned)((rows + kJtjWarps - 1) / kJtjWarps), kJtjWarps * 32, 0, (cudaStream_t)stream>>>(jac, logdet,
+                                                                                                                rows, d, n);
+  return check_launch("jtj_logdet_kernel");
+}

@@ -1,0 +1,390 @@
+// Fused rational-quadratic spline kernels (kernel (a) of BASELINE.json:north_star).
+//
+// One launch replaces ~60 ATen launches of the reference
+// (manifold_flow/transforms/splines/rational_quadratic.py:16-168, utils/various.py:472-474,
+// transforms/coupling.py:264-279,501-511): parameter slicing and 1/sqrt(hidden) pre-scale, both
+// softmaxes, knot construction, bin search, the RQ map (or its quadratic-root inverse), linear
+// tails, the per-sample log-det reduction and the coupling layer's identity pass-through.
+//
+// Two data layouts (see include/mflow_b200.h):
+//   "planes": parameters [O, C_t*P, I] - a warp reads 32 consecutive pixels of one parameter
+//             plane per load instruction: 128 B, fully coalesced, P independent loads in flight
+//             per thread.  This is also the generic strided kernel.
+//   "rows"  : parameters [O*C_t, P] contiguous - a CTA stages its rows through shared memory with
+//             coalesced loads and an odd row pitch (conflict-free per-thread row reads).
+// HBM-bound by design: 4*(P+2) algorithmic bytes per element forward, 4*(2P+3) backward.
+#include <stdarg.h>
+
+#include "rqs_math.cuh"
+
+namespace mflow {
+
+struct RqsArgs {
+  const float* x;
+  const float* x_out;  // backward + inverse only
+  const float* params;
+  float* y;            // forward: output; backward: g_in
+  float* lad_elem;     // forward: optional; backward: unused
+  float* lad_sample;
+  const float* lad_base;
+  int32_t* bins;
+  float* partial;      // [O, chunks]
+  unsigned int* counters;  // [O]
+  // backward
+  const float* g_out;
+  const float* g_lad_sample;
+  const float* g_lad_elem;
+  float* g_params;
+  int64_t n_outer, n_chan, n_inner;
+  int64_t x_so, x_sc, y_so, y_sc, p_so, p_sc, p_sp, p_si;
+  int64_t n_id_chan, id_off, id_sc;
+  int chunks;
+  RqsConsts c;
+};
+
+constexpr int kPlaneThreads = 256;
+constexpr int64_t kCounterBytes = 65536 * 4;  // one arrival counter per sample (planes layout: O <= 65535)
+
+// ---------------------------------------------------------------------------------------------
+// planes / generic layout, forward or inverse
+// grid = (chunks, O); CTA (chunk, o) walks elements [chunk*256, ...) of sample o with stride
+// chunks*256, so consecutive threads touch consecutive pixels of every parameter plane.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool INV>
+__global__ void __launch_bounds__(kPlaneThreads) rqs_planes_apply_kernel(const RqsArgs a) {
+  constexpr int P = 3 * K - 1;
+  __shared__ float red[kPlaneThreads / 32];
+  __shared__ int s_last;
+  const int64_t o = blockIdx.y;
+  const int64_t per_sample = a.n_chan * a.n_inner;
+  const float* xo = a.x + o * a.x_so;
+  float* yo = a.y + o * a.y_so;
+  const float* po = a.params + o * a.p_so;
+  float lad_acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample;
+       e += (int64_t)gridDim.x * kPlaneThreads) {
+    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
+    const float* pe = po + ch * a.p_sc + i * a.p_si;
+    float p[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * a.p_sp);
+    const float v = ldg_stream(xo + ch * a.x_sc + i);
+    float out, lad;
+    int bin;
+    rqs_eval<K, INV>(v, p, a.c, out, lad, bin);
+    stg_stream(yo + ch * a.y_sc + i, out);
+    if (a.lad_elem) stg_stream(a.lad_elem + o * per_sample + e, lad);
+    if (a.bins) a.bins[o * per_sample + e] = bin;
+    lad_acc += lad;
+  }
+  // identity half of the coupling layer: plain copy (coupling.py:116-118)
+  const int64_t n_id = a.n_id_chan * a.n_inner;
+  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += (int64_t)gridDim.x * kPlaneThreads) {
+    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
+    const int64_t off = a.id_off + ch * a.id_sc + i;
+    stg_stream(yo + off, ldg_stream(xo + off));
+  }
+  if (a.lad_sample == nullptr) return;
+  // deterministic per-sample reduction: CTA partial -> last-arriving CTA sums partials in order
+  const float bs = block_sum<kPlaneThreads>(lad_acc, red);
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + bs;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    a.partial[o * gridDim.x + blockIdx.x] = bs;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.counters[o], 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    float s = 0.f;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) s += __ldcg(a.partial + o * gridDim.x + j);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
+      a.counters[o] = 0u;  // leave the workspace ready for the next launch
+    }
+  }
+}
+
+// planes / generic layout, backward
+template <int K, bool INV>
+__global__ void __launch_bounds__(kPlaneThreads) rqs_planes_backward_kernel(const RqsArgs a) {
+  constexpr int P = 3 * K - 1;
+  const int64_t o = blockIdx.y;
+  const int64_t per_sample = a.n_chan * a.n_inner;
+  const float* xo = a.x + o * a.x_so;
+  const float* go = a.g_out ? a.g_out + o * a.y_so : nullptr;
+  float* gio = a.y + o * a.x_so;  // g_in uses the input tensor's indexing
+  const float* po = a.params + o * a.p_so;
+  float* gpo = a.g_params + o * a.p_so;
+  const float gl_s = a.g_lad_sample ? a.g_lad_sample[o] : 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample;
+       e += (int64_t)gridDim.x * kPlaneThreads) {
+    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
+    const int64_t poff = ch * a.p_sc + i * a.p_si;
+    float p[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) p[j] = ldg_stream(po + poff + j * a.p_sp);
+    const float v = ldg_stream(xo + ch * a.x_sc + i);
+    const float vo = INV ? ldg_stream(a.x_out + o * a.y_so + ch * a.y_sc + i) : 0.f;
+    const float g = go ? ldg_stream(go + ch * a.y_sc + i) : 0.f;
+    const float gl = gl_s + (a.g_lad_elem ? ldg_stream(a.g_lad_elem + o * per_sample + e) : 0.f);
+    float g_in;
+    float* gpe = gpo + poff;
+    const int64_t sp = a.p_sp;
+    rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * sp, val); });
+    stg_stream(gio + ch * a.x_sc + i, g_in);
+  }
+  const int64_t n_id = a.n_id_chan * a.n_inner;
+  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += (int64_t)gridDim.x * kPlaneThreads) {
+    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
+    const int64_t off = a.id_off + ch * a.id_sc + i;
+    stg_stream(gio + off, go ? ldg_stream(go + off) : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rows layout (vectors): parameters [O*C_t, P] contiguous.  A CTA owns G = 128 / C_t whole samples
+// (G*C_t <= 128 elements, one per thread), stages their G*C_t*P floats through shared memory with
+// coalesced loads, and reduces each sample's logabsdet sequentially in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 128;
+
+template <int K, bool INV, bool BWD>
+__global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, int samples_per_cta) {
+  constexpr int P = 3 * K - 1;
+  constexpr int PS = P | 1;  // odd pitch: thread t reads smem[t*PS + j] without bank conflicts
+  __shared__ float s_par[kRowThreads * PS];
+  __shared__ float s_lad[kRowThreads];
+  const int ct = (int)a.n_chan;
+  const int64_t o0 = (int64_t)blockIdx.x * samples_per_cta;
+  const int n_samp = (int)min((int64_t)samples_per_cta, a.n_outer - o0);
+  const int n_elem = n_samp * ct;
+  const int total = n_elem * P;
+  const float* src = a.params + o0 * a.p_so;
+  for (int idx = threadIdx.x; idx < total; idx += kRowThreads) {
+    const int r = idx / P, col = idx - r * P;
+    s_par[r * PS + col] = ldg_stream(src + idx);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const bool active = t < n_elem;
+  const int so = t / ct, ch = t - so * ct;
+  const int64_t o = o0 + so;
+  float p[P];
+  float lad = 0.f;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) p[j] = s_par[t * PS + j];
+    const float v = a.x[o * a.x_so + ch * a.x_sc];
+    if (!BWD) {
+      float out;
+      int bin;
+      rqs_eval<K, INV>(v, p, a.c, out, lad, bin);
+      a.y[o * a.y_so + ch * a.y_sc] = out;
+      if (a.lad_elem) a.lad_elem[o * ct + ch] = lad;
+      if (a.bins) a.bins[o * ct + ch] = bin;
+    } else {
+      const float vo = INV ? a.x_out[o * a.y_so + ch * a.y_sc] : 0.f;
+      const float g = a.g_out ? a.g_out[o * a.y_so + ch * a.y_sc] : 0.f;
+      const float gl = (a.g_lad_sample ? a.g_lad_sample[o] : 0.f) + (a.g_lad_elem ? a.g_lad_elem[o * ct + ch] : 0.f);
+      float g_in;
+      float* row = s_par + t * PS;  // the row is private to this thread: reuse it for the gradients
+      rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { row[j] = val; });
+      a.y[o * a.x_so + ch * a.x_sc] = g_in;
+    }
+  }
+  // identity features of these samples (coupling merge / its gradient)
+  for (int idx = t; idx < n_samp * (int)a.n_id_chan; idx += kRowThreads) {
+    const int s2 = idx / (int)a.n_id_chan, c2 = idx - s2 * (int)a.n_id_chan;
+    if (!BWD) {
+      a.y[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] = a.x[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc];
+    } else {
+      a.y[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc] =
+          a.g_out ? a.g_out[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] : 0.f;
+    }
+  }
+  if (!BWD) {
+    if (a.lad_sample == nullptr) return;
+    s_lad[t] = lad;
+    __syncthreads();
+    if (active && ch == 0) {
+      float s = 0.f;
+      for (int j = 0; j < ct; ++j) s += s_lad[t + j];
+      a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
+    }
+  } else {
+    __syncthreads();
+    float* dst = a.g_params + o0 * a.p_so;
+    for (int idx = threadIdx.x; idx < total; idx += kRowThreads) {
+      const int r = idx / P, col = idx - r * P;
+      stg_stream(dst + idx, s_par[r * PS + col]);
+    }
+  }
+}
+
+template <int K>
+__global__ void rqs_search_kernel(const float* knots, const float* values, int32_t* bins, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float kn[K + 1];
+#pragma unroll
+  for (int j = 0; j <= K; ++j) kn[j] = knots[i * (K + 1) + j];
+  float lo, hi;
+  const float v = values[i];
+  // same closed-interval rule as the spline kernels; values outside the knots get -1
+  bins[i] = (v >= kn[0] && v <= kn[K]) ? rqs_search<K>(kn, v, lo, hi) : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool fill_args(const mflow_rqs_desc* d, RqsArgs& a) {
+  a.n_outer = d->n_outer;
+  a.n_chan = d->n_chan;
+  a.n_inner = d->n_inner;
+  a.x_so = d->x_so; a.x_sc = d->x_sc; a.y_so = d->y_so; a.y_sc = d->y_sc;
+  a.p_so = d->p_so; a.p_sc = d->p_sc; a.p_sp = d->p_sp; a.p_si = d->p_si;
+  a.n_id_chan = d->n_id_chan; a.id_off = d->id_off; a.id_sc = d->id_sc;
+  const int K = d->num_bins;
+  const double T = (double)d->tail_bound;
+  RqsConsts& c = a.c;
+  c.tail = (float)T;
+  c.lo = (float)(-T);
+  c.span = (float)(T - (-T));
+  c.min_w = d->min_bin_width;
+  c.min_h = d->min_bin_height;
+  c.min_d = d->min_derivative;
+  // Python evaluates (1 - min * K) and log(exp(1 - min_d) - 1) in double, torch rounds them once
+  c.cfac_w = (float)(1.0 - (double)d->min_bin_width * K);
+  c.cfac_h = (float)(1.0 - (double)d->min_bin_height * K);
+  c.edge = (float)log(exp(1.0 - (double)d->min_derivative) - 1.0);
+  c.divisor = d->wh_divisor;
+  c.rcp_divisor = 1.0f / d->wh_divisor;
+  c.use_divisor = d->wh_divisor != 1.0f;
+  return true;
+}
+
+static int plane_chunks(const mflow_rqs_desc* d) {
+  // CTAs per sample: one per 256 elements, capped so the grid stays near 16 CTAs per SM (each
+  // thread then loops); never more than 1024 partial sums per sample.
+  const int64_t per_sample = d->n_chan * d->n_inner;
+  int64_t chunks = (per_sample + kPlaneThreads - 1) / kPlaneThreads;
+  const int64_t cap = ((int64_t)kNumSMs * 16 + d->n_outer - 1) / (d->n_outer > 0 ? d->n_outer : 1);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 1024) chunks = 1024;
+  return (int)chunks;
+}
+
+static bool rows_fast_path(const mflow_rqs_desc* d) {
+  const int P = 3 * d->num_bins - 1;
+  return d->n_inner == 1 && d->p_sp == 1 && d->p_sc == P && d->p_so == d->n_chan * P && d->n_chan <= kRowThreads &&
+         d->n_id_chan <= 4 * kRowThreads;
+}
+
+#define MFLOW_DISPATCH_K(K_, ...)                    \
+  switch (K_) {                                      \
+    case 4: { constexpr int K = 4; __VA_ARGS__; break; }   \
+    case 5: { constexpr int K = 5; __VA_ARGS__; break; }   \
+    case 6: { constexpr int K = 6; __VA_ARGS__; break; }   \
+    case 8: { constexpr int K = 8; __VA_ARGS__; break; }   \
+    case 10: { constexpr int K = 10; __VA_ARGS__; break; } \
+    case 11: { constexpr int K = 11; __VA_ARGS__; break; } \
+    case 12: { constexpr int K = 12; __VA_ARGS__; break; } \
+    case 16: { constexpr int K = 16; __VA_ARGS__; break; } \
+    default:                                         \
+      set_error("num_bins=%d is not compiled in (supported: 4,5,6,8,10,11,12,16)", (int)(K_)); \
+      return MFLOW_E_BADARG;                         \
+  }
+
+static int validate(const mflow_rqs_desc* d) {
+  MFLOW_REQUIRE(d != nullptr, "null descriptor");
+  MFLOW_REQUIRE(d->n_outer >= 0 && d->n_chan >= 1 && d->n_inner >= 1, "bad extents");
+  MFLOW_REQUIRE(d->n_outer <= 65535 * 1024LL, "n_outer too large");
+  MFLOW_REQUIRE(d->tail_bound > 0.f, "tail_bound must be positive");
+  MFLOW_REQUIRE(d->wh_divisor > 0.f, "wh_divisor must be positive");
+  MFLOW_REQUIRE((double)d->min_bin_width * d->num_bins <= 1.0, "Minimal bin width too large for the number of bins");
+  MFLOW_REQUIRE((double)d->min_bin_height * d->num_bins <= 1.0, "Minimal bin height too large for the number of bins");
+  return MFLOW_OK;
+}
+
+}  // namespace mflow
+
+using namespace mflow;
+
+extern "C" MFLOW_API int64_t mflow_rqs_workspace_bytes(const mflow_rqs_desc* d) {
+  if (d == nullptr || d->n_outer <= 0) return 16;
+  const int chunks = plane_chunks(d);
+  return kCounterBytes + (int64_t)d->n_outer * chunks * 4 + 16;
+}
+
+extern "C" MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* d, const float* x, const float* params, float* y, float* lad_elem,
+                               float* lad_sample, const float* lad_base, int32_t* bins, void* workspace, void* stream) {
+  if (int rc = validate(d)) return rc;
+  if (d->n_outer == 0) return MFLOW_OK;
+  MFLOW_REQUIRE(x && params && y, "null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  RqsArgs a{};
+  fill_args(d, a);
+  a.x = x; a.params = params; a.y = y; a.lad_elem = lad_elem; a.lad_sample = lad_sample; a.lad_base = lad_base;
+  a.bins = bins;
+  if (rows_fast_path(d)) {
+    const int spc = kRowThreads / (int)d->n_chan;
+    const unsigned grid = (unsigned)((d->n_outer + spc - 1) / spc);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rows_kernel<K, true, false><<<grid, kRowThreads, 0, st>>>(a, spc);
+                     else rqs_rows_kernel<K, false, false><<<grid, kRowThreads, 0, st>>>(a, spc));
+    return check_launch("rqs_rows_kernel");
+  }
+  MFLOW_REQUIRE(d->n_outer <= 65535, "planes layout: n_outer must be <= 65535 (split the batch)");
+  const int chunks = plane_chunks(d);
+  a.chunks = chunks;
+  if (lad_sample && chunks > 1) {
+    MFLOW_REQUIRE(workspace != nullptr, "workspace required for the per-sample reduction");
+    a.counters = (unsigned int*)workspace;  // fixed-size counter region first: stays zero between launches
+    a.partial = (float*)((char*)workspace + kCounterBytes);
+  }
+  dim3 grid(chunks, (unsigned)d->n_outer);
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_apply_kernel<K, true><<<grid, kPlaneThreads, 0, st>>>(a);
+                   else rqs_planes_apply_kernel<K, false><<<grid, kPlaneThreads, 0, st>>>(a));
+  return check_launch("rqs_planes_apply_kernel");
+}
+
+extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float* x_in, const float* x_out, const float* params,
+                                  const float* g_out, const float* g_lad_sample, const float* g_lad_elem, float* g_in,
+                                  float* g_params, void* stream) {
+  if (int rc = validate(d)) return rc;
+  if (d->n_outer == 0) return MFLOW_OK;
+  MFLOW_REQUIRE(x_in && params && g_in && g_params, "null tensor pointer");
+  MFLOW_REQUIRE(!d->inverse || x_out, "inverse backward needs the output of the apply call");
+  cudaStream_t st = (cudaStream_t)stream;
+  RqsArgs a{};
+  fill_args(d, a);
+  a.x = x_in; a.x_out = x_out; a.params = params; a.y = g_in; a.g_out = g_out; a.g_lad_sample = g_lad_sample;
+  a.g_lad_elem = g_lad_elem; a.g_params = g_params;
+  if (rows_fast_path(d)) {
+    const int spc = kRowThreads / (int)d->n_chan;
+    const unsigned grid = (unsigned)((d->n_outer + spc - 1) / spc);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rows_kernel<K, true, true><<<grid, kRowThreads, 0, st>>>(a, spc);
+                     else rqs_rows_kernel<K, false, true><<<grid, kRowThreads, 0, st>>>(a, spc));
+    return check_launch("rqs_rows_kernel(bwd)");
+  }
+  MFLOW_REQUIRE(d->n_outer <= 65535, "planes layout: n_outer must be <= 65535 (split the batch)");
+  dim3 grid(plane_chunks(d), (unsigned)d->n_outer);
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_backward_kernel<K, true><<<grid, kPlaneThreads, 0, st>>>(a);
+                   else rqs_planes_backward_kernel<K, false><<<grid, kPlaneThreads, 0, st>>>(a));
+  return check_launch("rqs_planes_backward_kernel");
+}
+
+extern "C" MFLOW_API int mflow_rqs_search(const float* knots, const float* values, int32_t* bins, int64_t n, int32_t num_bins,
+                                void* stream) {
+  MFLOW_REQUIRE(knots && values && bins, "null tensor pointer");
+  if (n == 0) return MFLOW_OK;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  MFLOW_DISPATCH_K(num_bins, rqs_search_kernel<K><<<grid, 128, 0, (cudaStream_t)stream>>>(knots, values, bins, n));
+  return check_launch("rqs_search_kernel");
+}

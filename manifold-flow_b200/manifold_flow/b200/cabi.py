@@ -1,0 +1,174 @@
+"""ctypes binding of ``libmflow_b200.so`` (C ABI declared in ``include/mflow_b200.h``).
+
+The library is loaded lazily: building a model (``nn.Module`` construction, ``state_dict``
+handling) works on a CPU-only box, but the first kernel call without the library or without a
+CUDA tensor raises - there is no CPU fallback and no eager-PyTorch fallback on this path.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "lib", "libmflow_b200.so")
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+c_f32p = ctypes.c_void_p
+i64 = ctypes.c_int64
+i32 = ctypes.c_int32
+f32 = ctypes.c_float
+
+
+class RqsDesc(ctypes.Structure):
+    """mflow_rqs_desc"""
+
+    _fields_ = [
+        ("n_outer", i64), ("n_chan", i64), ("n_inner", i64),
+        ("x_so", i64), ("x_sc", i64), ("y_so", i64), ("y_sc", i64),
+        ("p_so", i64), ("p_sc", i64), ("p_sp", i64), ("p_si", i64),
+        ("num_bins", i32), ("inverse", i32),
+        ("tail_bound", f32), ("min_bin_width", f32), ("min_bin_height", f32), ("min_derivative", f32),
+        ("wh_divisor", f32),
+        ("n_id_chan", i64), ("id_off", i64), ("id_sc", i64),
+    ]
+
+
+class MixDesc(ctypes.Structure):
+    """mflow_mix_desc"""
+
+    _fields_ = [
+        ("n_outer", i64), ("n_chan", i64), ("n_inner", i64),
+        ("x_so", i64), ("x_sc", i64), ("x_si", i64),
+        ("y_so", i64), ("y_sc", i64), ("y_si", i64),
+    ]
+
+
+_SIGNATURES = {
+    "mflow_version": (ctypes.c_int, []),
+    "mflow_last_error_string": (ctypes.c_char_p, []),
+    "mflow_check_device": (ctypes.c_int, []),
+    "mflow_rqs_workspace_bytes": (i64, [ctypes.POINTER(RqsDesc)]),
+    "mflow_rqs_apply": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
+    "mflow_rqs_backward": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
+    "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
+    "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),
+    "mflow_chanmix_wgrad_workspace_bytes": (i64, [ctypes.POINTER(MixDesc)]),
+    "mflow_chanmix_wgrad": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 6),
+    "mflow_squeeze2x2": (ctypes.c_int, [c_f32p, c_f32p, i64, i64, i64, i64, i32, f32, f32, c_f32p]),
+    "mflow_affine_scalar": (ctypes.c_int, [c_f32p, c_f32p, i64, f32, f32, i32, c_f32p]),
+    "mflow_permute_rows": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, c_f32p]),
+    "mflow_logtanh_apply": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, i32, f32, c_f32p]),
+    "mflow_logtanh_backward": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, i64, i64, i32, f32, c_f32p]),
+    "mflow_gauss_logprob": (ctypes.c_int, [c_f32p, i64, i64, c_f32p, i64, i64, f32, f32, c_f32p, c_f32p, c_f32p, i64, c_f32p]),
+    "mflow_gauss_logprob_backward": (ctypes.c_int, [c_f32p, i64, i64, c_f32p, i64, i64, f32, f32, c_f32p, c_f32p, c_f32p, i64, c_f32p]),
+    "mflow_jtj_logdet": (ctypes.c_int, [c_f32p, c_f32p, i64, i32, i32, c_f32p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class MflowError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it was never built (no fallback)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise MflowError(
+                        f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(make -C manifold-flow_b200/csrc). The B200 path has no CPU or eager fallback."
+                    )
+                handle = ctypes.CDLL(_LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mflow_last_error_string().decode()
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}" if what else msg)
+        raise MflowError(f"{what}: {msg} (code {rc})")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MflowError(
+                "manifold_flow (B200 build) runs on CUDA tensors only: got a tensor on "
+                f"{t.device}. Move the model and its inputs to the GPU (there is no CPU fallback)."
+            )
+        if t is not None and t.dtype != torch.float32:
+            raise MflowError(f"the B200 kernels compute in float32; got {t.dtype}")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces = {}
+
+
+def workspace(tag, nbytes, device):
+    """Zero-initialised scratch, cached per (purpose, device, stream).  The kernels keep their
+    arrival counters in a fixed region at the start and leave them zeroed."""
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def count_launch(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ---- optional per-kernel device timing (bench.py: roofline.achieved) -----------------------------
+class KernelTimer:
+    """Brackets selected launches with CUDA events on the launching stream and accumulates, per tag,
+    the device time and the algorithmic bytes.  Off unless bench.py installs one."""
+
+    def __init__(self):
+        self.records = []  # (tag, bytes, start_event, end_event)
+
+    def begin(self, tag, nbytes):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return (tag, nbytes, ev)
+
+    def end(self, token):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((token[0], token[1], token[2], ev))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, nbytes, e0, e1 in self.records:
+            d = out.setdefault(tag, dict(launches=0, ms=0.0, bytes=0))
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+        return out
+
+
+kernel_timer = None

@@ -1,0 +1,16 @@
+"""Run-time switches of the B200 back end."""
+import os
+
+
+class _Config:
+    # "fp32": conditioner GEMMs/convolutions reproduce the reference's fp32 results (parity mode)
+    # "tf32": single-pass TF32 tensor-core math (throughput sweeps; not parity-clean)
+    conditioner_math = os.environ.get("MFLOW_CONDITIONER_MATH", "fp32")
+    # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch
+    fuse_linear_glue = os.environ.get("MFLOW_FUSE_GLUE", "1") != "0"
+    # full_jacobian=True: the reference's Permutation Jacobian is the transpose of the exact one
+    # (permutations.py:49); False reproduces the reference (parity), True is mathematically exact
+    exact_permutation_jacobian = os.environ.get("MFLOW_EXACT_PERM_JACOBIAN", "0") == "1"
+
+
+config = _Config()

@@ -1,0 +1,418 @@
+"""Autograd functions over the C ABI of ``libmflow_b200.so``.
+
+Each function is one fused launch (forward) plus one fused launch (backward); inputs must be
+float32 CUDA tensors.  Nothing here falls back to eager PyTorch: a missing library, a CPU tensor
+or an unsupported shape raises.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import cabi
+from .cabi import MixDesc, RqsDesc, check, lib, ptr, require_cuda, stream
+
+
+def _c(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# (a) rational-quadratic spline
+# --------------------------------------------------------------------------------------------
+class SplineGeometry:
+    """Where the transformed (and identity) features of a coupling layer live inside the full
+    activation tensor, as an arithmetic progression: feature c at ``offset + c * step`` (in units
+    of channels / features).  All masks the reference factories build are of this form
+    (alternating: utils/various.py:410-421; mid split: :424-434)."""
+
+    __slots__ = ("n_transform", "t_offset", "t_step", "n_identity", "i_offset", "i_step")
+
+    def __init__(self, n_transform, t_offset, t_step, n_identity, i_offset, i_step):
+        self.n_transform, self.t_offset, self.t_step = n_transform, t_offset, t_step
+        self.n_identity, self.i_offset, self.i_step = n_identity, i_offset, i_step
+
+    @staticmethod
+    def from_indices(transform_idx, identity_idx):
+        def prog(idx):
+            idx = [int(v) for v in idx]
+            if len(idx) == 0:
+                return 0, 1
+            step = idx[1] - idx[0] if len(idx) > 1 else 1
+            if step < 1 or any(idx[j + 1] - idx[j] != step for j in range(len(idx) - 1)):
+                return None
+            return idx[0], step
+
+        t, i = prog(transform_idx), prog(identity_idx)
+        if t is None or i is None:
+            return None
+        return SplineGeometry(len(transform_idx), t[0], t[1], len(identity_idx), i[0], i[1])
+
+
+def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
+    """Descriptor for a coupling layer on the full activation tensor ``x`` ([B, C, H, W] or [B, D],
+    contiguous) and the conditioner output ``params`` ([B, C_t*P, H, W] or [B, C_t*P], contiguous)."""
+    p = 3 * num_bins - 1
+    d = RqsDesc()
+    b = x.shape[0]
+    feats = x.shape[1]
+    inner = x.shape[2] * x.shape[3] if x.dim() == 4 else 1
+    d.n_outer, d.n_chan, d.n_inner = b, geom.n_transform, inner
+    d.x_so = d.y_so = feats * inner
+    d.x_sc = d.y_sc = geom.t_step * inner
+    d.p_so = geom.n_transform * p * inner
+    d.p_sc = p * inner
+    d.p_sp = inner
+    d.p_si = 1
+    d.num_bins, d.inverse = num_bins, int(bool(inverse))
+    d.tail_bound, d.min_bin_width, d.min_bin_height, d.min_derivative = tail_bound, min_w, min_h, min_d
+    d.wh_divisor = divisor
+    d.n_id_chan, d.id_off, d.id_sc = geom.n_identity, geom.i_offset * inner, geom.i_step * inner
+    return d, geom.t_offset * inner
+
+
+def _rqs_bytes(d, backward):
+    """Algorithmic HBM bytes of one spline launch: forward / inverse read P params + x
+    and write y per element (+ 4 B per sample for the log-det); backward reads params, x, g_y and
+    writes g_params, g_x."""
+    p = 3 * d.num_bins - 1
+    n = d.n_outer * d.n_chan * d.n_inner
+    return n * 4 * (2 * p + 3) if backward else n * 4 * (p + 2) + 4 * d.n_outer
+
+
+class _RqsCoupling(torch.autograd.Function):
+    """(x_full, params) -> (y_full, logabsdet[B]).  coupling.py:58-185 + rational_quadratic.py."""
+
+    @staticmethod
+    def forward(ctx, x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
+        require_cuda(x, params)
+        x, params = _c(x), _c(params)
+        p = 3 * num_bins - 1
+        expected = x.shape[0] * geom.n_transform * p * (x.shape[2] * x.shape[3] if x.dim() == 4 else 1)
+        if params.numel() != expected:
+            raise ValueError(f"conditioner output has {params.numel()} values, expected {expected}")
+        desc, off = _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse)
+        y = torch.empty_like(x)
+        lad = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        ws = cabi.workspace("rqs", lib().mflow_rqs_workspace_bytes(ctypes.byref(desc)), x.device)
+        xo = ctypes.c_void_p(x.data_ptr() + 4 * off)
+        yo = ctypes.c_void_p(y.data_ptr() + 4 * off)
+        # identity features are addressed relative to the same shifted base
+        desc.id_off -= off
+        tok = cabi.kernel_timer.begin("rqs_inv" if inverse else "rqs_fwd", _rqs_bytes(desc, False)) if cabi.kernel_timer else None
+        check(lib().mflow_rqs_apply(ctypes.byref(desc), xo, ptr(params), yo, None, ptr(lad), None, None, ptr(ws), stream()),
+              "mflow_rqs_apply")
+        if tok:
+            cabi.kernel_timer.end(tok)
+        cabi.count_launch()
+        ctx.desc, ctx.off = desc, off
+        ctx.save_for_backward(x, params, y if inverse else None)
+        return y, lad
+
+    @staticmethod
+    def backward(ctx, g_y, g_lad):
+        x, params, y = ctx.saved_tensors
+        desc, off = ctx.desc, ctx.off
+        g_y = None if g_y is None else _c(g_y)
+        g_lad = None if g_lad is None else _c(g_lad)
+        g_x = torch.empty_like(x)
+        g_p = torch.empty_like(params)
+        sh = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() + 4 * off)
+        tok = cabi.kernel_timer.begin("rqs_bwd", _rqs_bytes(desc, True)) if cabi.kernel_timer else None
+        check(lib().mflow_rqs_backward(ctypes.byref(desc), sh(x), sh(y), ptr(params), sh(g_y), ptr(g_lad), None, sh(g_x),
+                                       ptr(g_p), stream()), "mflow_rqs_backward")
+        if tok:
+            cabi.kernel_timer.end(tok)
+        cabi.count_launch()
+        return (g_x, g_p) + (None,) * 8
+
+
+def rqs_coupling(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
+    return _RqsCoupling.apply(x, params, geom, num_bins, float(tail_bound), float(min_w), float(min_h), float(min_d),
+                              float(divisor), bool(inverse))
+
+
+class _RqsElementwise(torch.autograd.Function):
+    """Flat [N] inputs with [N, 3K-1] parameter rows -> (outputs[N], logabsdet[N]): the function-level
+    API ``unconstrained_rational_quadratic_spline`` (rational_quadratic.py:16-64)."""
+
+    @staticmethod
+    def forward(ctx, x, params, num_bins, tail_bound, min_w, min_h, min_d, inverse, want_bins):
+        require_cuda(x, params)
+        x, params = _c(x), _c(params)
+        n, p = x.numel(), 3 * num_bins - 1
+        d = RqsDesc()
+        d.n_outer, d.n_chan, d.n_inner = n, 1, 1
+        d.x_so = d.y_so = 1
+        d.x_sc = d.y_sc = 1
+        d.p_so, d.p_sc, d.p_sp, d.p_si = p, p, 1, 1
+        d.num_bins, d.inverse = num_bins, int(bool(inverse))
+        d.tail_bound, d.min_bin_width, d.min_bin_height, d.min_derivative, d.wh_divisor = tail_bound, min_w, min_h, min_d, 1.0
+        y = torch.empty_like(x)
+        lad = torch.empty_like(x)
+        bins = torch.empty(n, dtype=torch.int32, device=x.device) if want_bins else None
+        check(lib().mflow_rqs_apply(ctypes.byref(d), ptr(x), ptr(params), ptr(y), ptr(lad), None, None, ptr(bins), None, stream()),
+              "mflow_rqs_apply")
+        cabi.count_launch()
+        ctx.desc = d
+        ctx.save_for_backward(x, params, y if inverse else None)
+        if want_bins:
+            ctx.mark_non_differentiable(bins)
+            return y, lad, bins
+        return y, lad
+
+    @staticmethod
+    def backward(ctx, g_y, g_lad, *_):
+        x, params, y = ctx.saved_tensors
+        g_x, g_p = torch.empty_like(x), torch.empty_like(params)
+        check(lib().mflow_rqs_backward(ctypes.byref(ctx.desc), ptr(x), ptr(y), ptr(params), ptr(None if g_y is None else _c(g_y)),
+                                       None, ptr(None if g_lad is None else _c(g_lad)), ptr(g_x), ptr(g_p), stream()),
+              "mflow_rqs_backward")
+        cabi.count_launch()
+        return (g_x, g_p) + (None,) * 7
+
+
+def rqs_elementwise(x, params, num_bins, tail_bound, min_w=1e-3, min_h=1e-3, min_d=1e-3, inverse=False, return_bins=False):
+    return _RqsElementwise.apply(x, params, num_bins, float(tail_bound), float(min_w), float(min_h), float(min_d), bool(inverse),
+                                 bool(return_bins))
+
+
+def rqs_search(knots, values):
+    """The kernels' bin search on given knots ([n, K+1], [n]) -> int32 [n] (test entry)."""
+    require_cuda(knots, values)
+    knots, values = _c(knots), _c(values)
+    bins = torch.empty(values.numel(), dtype=torch.int32, device=values.device)
+    check(lib().mflow_rqs_search(ptr(knots), ptr(values), ptr(bins), values.numel(), knots.shape[-1] - 1, stream()), "mflow_rqs_search")
+    cabi.count_launch()
+    return bins
+
+
+# --------------------------------------------------------------------------------------------
+# (c) linear glue
+# --------------------------------------------------------------------------------------------
+def _mix_desc(x):
+    d = MixDesc()
+    if x.dim() == 4:
+        b, c, h, w = x.shape
+        d.n_outer, d.n_chan, d.n_inner = b, c, h * w
+        d.x_so = d.y_so = c * h * w
+        d.x_sc = d.y_sc = h * w
+        d.x_si = d.y_si = 1
+    else:
+        b, c = x.shape
+        d.n_outer, d.n_chan, d.n_inner = b, c, 1
+        d.x_so = d.y_so = c
+        d.x_sc = d.y_sc = 1
+        d.x_si = d.y_si = 1
+    return d
+
+
+class _ChanMix(torch.autograd.Function):
+    """y[b, :, hw] = M x[b, :, hw] + m for [B, C, H, W] or [B, C] activations."""
+
+    @staticmethod
+    def forward(ctx, x, mat, bias):
+        require_cuda(x, mat, bias)
+        x, mat, bias = _c(x), _c(mat), _c(bias)
+        d = _mix_desc(x)
+        y = torch.empty_like(x)
+        check(lib().mflow_chanmix_apply(ctypes.byref(d), ptr(x), ptr(mat), ptr(bias), ptr(y), stream()), "mflow_chanmix_apply")
+        cabi.count_launch()
+        ctx.desc = d
+        ctx.save_for_backward(x, mat)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, mat = ctx.saved_tensors
+        d = ctx.desc
+        g_y = _c(g_y)
+        g_x = g_mat = g_bias = None
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty_like(x)
+            mat_t = mat.t().contiguous()
+            check(lib().mflow_chanmix_apply(ctypes.byref(d), ptr(g_y), ptr(mat_t), None, ptr(g_x), stream()), "mflow_chanmix_apply")
+            cabi.count_launch()
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            g_mat = torch.empty_like(mat)
+            g_bias = torch.empty(mat.shape[0], dtype=torch.float32, device=mat.device)
+            ws = cabi.workspace("wgrad", lib().mflow_chanmix_wgrad_workspace_bytes(ctypes.byref(d)), x.device)
+            check(lib().mflow_chanmix_wgrad(ctypes.byref(d), ptr(x), ptr(g_y), ptr(g_mat), ptr(g_bias), ptr(ws), stream()),
+                  "mflow_chanmix_wgrad")
+            cabi.count_launch()
+            if not ctx.has_bias:
+                g_bias = None
+        return g_x, g_mat, g_bias
+
+
+def chanmix(x, mat, bias=None):
+    return _ChanMix.apply(x, mat, bias)
+
+
+class _Squeeze(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inverse, scale, shift):
+        require_cuda(x)
+        x = _c(x)
+        b, c, h, w = x.shape
+        if inverse:
+            if c < 4 or c % 4 != 0:
+                raise ValueError("Invalid number of channel dimensions.")
+            y = torch.empty((b, c // 4, h * 2, w * 2), dtype=x.dtype, device=x.device)
+        else:
+            if h % 2 != 0 or w % 2 != 0:
+                raise ValueError("Input image size not compatible with the factor.")
+            y = torch.empty((b, c * 4, h // 2, w // 2), dtype=x.dtype, device=x.device)
+        check(lib().mflow_squeeze2x2(ptr(x), ptr(y), b, c, h, w, int(inverse), scale, shift, stream()), "mflow_squeeze2x2")
+        cabi.count_launch()
+        ctx.inverse, ctx.scale = inverse, scale
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        g_y = _c(g_y)
+        b, c, h, w = g_y.shape
+        # forward y = s * squeeze(x) + t  ->  g_x = unsqueeze(g_y) * s ; inverse: g_x = squeeze(g_y) / s
+        if ctx.inverse:
+            g_x = torch.empty((b, c * 4, h // 2, w // 2), dtype=g_y.dtype, device=g_y.device)
+            check(lib().mflow_squeeze2x2(ptr(g_y), ptr(g_x), b, c, h, w, 0, 1.0 / ctx.scale, 0.0, stream()), "mflow_squeeze2x2")
+        else:
+            g_x = torch.empty((b, c // 4, h * 2, w * 2), dtype=g_y.dtype, device=g_y.device)
+            check(lib().mflow_squeeze2x2(ptr(g_y), ptr(g_x), b, c, h, w, 1, 1.0 / ctx.scale, 0.0, stream()), "mflow_squeeze2x2")
+        cabi.count_launch()
+        return g_x, None, None, None
+
+
+def squeeze2x2(x, inverse=False, scale=1.0, shift=0.0):
+    return _Squeeze.apply(x, bool(inverse), float(scale), float(shift))
+
+
+class _AffineScalar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, shift, inverse):
+        require_cuda(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        check(lib().mflow_affine_scalar(ptr(x), ptr(y), x.numel(), scale, shift, int(inverse), stream()), "mflow_affine_scalar")
+        cabi.count_launch()
+        ctx.factor = (1.0 / scale) if inverse else scale
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        g_y = _c(g_y)
+        g_x = torch.empty_like(g_y)
+        check(lib().mflow_affine_scalar(ptr(g_y), ptr(g_x), g_y.numel(), ctx.factor, 0.0, 0, stream()), "mflow_affine_scalar")
+        cabi.count_launch()
+        return g_x, None, None, None
+
+
+def affine_scalar(x, scale, shift, inverse=False):
+    return _AffineScalar.apply(x, float(scale), float(shift), bool(inverse))
+
+
+class _PermuteRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, perm, inv_perm):
+        require_cuda(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        check(lib().mflow_permute_rows(ptr(x), ptr(perm), ptr(y), x.shape[0], x.shape[1], stream()), "mflow_permute_rows")
+        cabi.count_launch()
+        ctx.save_for_backward(inv_perm)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        (inv_perm,) = ctx.saved_tensors
+        g_y = _c(g_y)
+        g_x = torch.empty_like(g_y)
+        check(lib().mflow_permute_rows(ptr(g_y), ptr(inv_perm), ptr(g_x), g_y.shape[0], g_y.shape[1], stream()), "mflow_permute_rows")
+        cabi.count_launch()
+        return g_x, None, None
+
+
+def permute_rows(x, perm, inv_perm):
+    """y[:, j] = x[:, perm[j]] for a 2-D x (int64 CUDA index tensors)."""
+    return _PermuteRows.apply(x, perm, inv_perm)
+
+
+class _LogTanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inverse, cut_point):
+        require_cuda(x)
+        x = _c(x)
+        rows, n = x.shape[0], x[0].numel()
+        y = torch.empty_like(x)
+        lad = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib().mflow_logtanh_apply(ptr(x), ptr(y), ptr(lad), rows, n, int(inverse), cut_point, stream()), "mflow_logtanh_apply")
+        cabi.count_launch()
+        ctx.inverse, ctx.cut = inverse, cut_point
+        ctx.save_for_backward(x)
+        return y, lad
+
+    @staticmethod
+    def backward(ctx, g_y, g_lad):
+        (x,) = ctx.saved_tensors
+        g_x = torch.empty_like(x)
+        check(lib().mflow_logtanh_backward(ptr(x), ptr(None if g_y is None else _c(g_y)), ptr(None if g_lad is None else _c(g_lad)),
+                                           ptr(g_x), x.shape[0], x[0].numel(), int(ctx.inverse), ctx.cut, stream()),
+              "mflow_logtanh_backward")
+        cabi.count_launch()
+        return g_x, None, None
+
+
+def logtanh(x, inverse=False, cut_point=1.0):
+    return _LogTanh.apply(x, bool(inverse), float(cut_point))
+
+
+# --------------------------------------------------------------------------------------------
+# likelihood epilogues
+# --------------------------------------------------------------------------------------------
+class _GaussLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, v, add0, add1, eps, clip):
+        require_cuda(u, v, add0, add1)
+        if u.stride(-1) != 1 or (v is not None and v.stride(-1) != 1):
+            u, v = u.contiguous(), (None if v is None else v.contiguous())
+        rows, n_u = u.shape
+        n_v = 0 if v is None else v.shape[1]
+        out = torch.empty(rows, dtype=torch.float32, device=u.device)
+        check(lib().mflow_gauss_logprob(ptr(u), n_u, u.stride(0), ptr(v), n_v, 0 if v is None else v.stride(0), eps, clip,
+                                        ptr(None if add0 is None else _c(add0)), ptr(None if add1 is None else _c(add1)), ptr(out),
+                                        rows, stream()), "mflow_gauss_logprob")
+        cabi.count_launch()
+        ctx.eps, ctx.clip = eps, clip
+        ctx.save_for_backward(u, v)
+        ctx.has = (add0 is not None, add1 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        u, v = ctx.saved_tensors
+        g = _c(g)
+        rows, n_u = u.shape
+        n_v = 0 if v is None else v.shape[1]
+        g_u = torch.empty((rows, n_u), dtype=torch.float32, device=u.device)
+        g_v = None if v is None else torch.empty((rows, n_v), dtype=torch.float32, device=u.device)
+        check(lib().mflow_gauss_logprob_backward(ptr(u), n_u, u.stride(0), ptr(v), n_v, 0 if v is None else v.stride(0), ctx.eps,
+                                                 ctx.clip, ptr(g), ptr(g_u), ptr(g_v), rows, stream()), "mflow_gauss_logprob_backward")
+        cabi.count_launch()
+        return g_u, g_v, (g if ctx.has[0] else None), (g if ctx.has[1] else None), None, None
+
+
+def gauss_logprob(u, v=None, eps=1.0, clip=None, add0=None, add1=None):
+    """logN(u; 0, 1) [+ logN(clamp(v); 0, eps^2)] [+ add0] [+ add1], per row."""
+    return _GaussLogProb.apply(u, v, add0, add1, float(eps), float(clip) if clip else 0.0)
+
+
+def jtj_logdet(jac):
+    """log det(J^T J) per sample for J [B, D, n], n <= 32 (no gradient)."""
+    require_cuda(jac)
+    jac = _c(jac.detach())
+    b, d, n = jac.shape
+    out = torch.empty(b, dtype=torch.float32, device=jac.device)
+    check(lib().mflow_jtj_logdet(ptr(jac), ptr(out), b, d, n, stream()), "mflow_jtj_logdet")
+    cabi.count_launch()
+    return out

@@ -1,0 +1,98 @@
+"""Chain evaluation with linear-glue fusion (kernel (c) of the north star).
+
+ActNorm, the channel permutation + LU map of the 1x1 convolution, ``RandomPermutation`` +
+``LULinear`` on vectors are all per-pixel affine maps over the channel axis.  A run of such layers is
+composed into ONE dense C x C matrix (a handful of tiny differentiable torch ops on [C, C] tensors,
+rebuilt once per optimizer step) and applied by ONE ``mflow_chanmix_apply`` launch that reads and
+writes the activation exactly once - the reference issues ~10 ATen launches and 4 activation
+round trips for the same step (normalization.py:99-131, conv.py:16-55, lu.py:44-95,
+permutations.py:73).
+"""
+import torch
+
+from ..b200 import ops
+from ..b200.config import config
+
+MAX_FUSED_CHANNELS = 96  # chanmix weight-gradient kernel limit (shared memory)
+
+_pass_id = 0
+
+
+def begin_pass():
+    """Called at the start of every model-level forward: dense L/U and composed matrices built
+    under autograd are reused by all transforms evaluated within the same pass."""
+    global _pass_id
+    _pass_id += 1
+    return _pass_id
+
+
+def current_pass():
+    return _pass_id
+
+
+def _linear_capable(t, x):
+    return getattr(t, "_affine_map", None) is not None and t._can_fuse(x)
+
+
+def apply_affine(maps, x):
+    """Compose a run of per-pixel affine maps (M, m, logabsdet) and apply them in one launch."""
+    mat, bias, lad = maps[0]
+    for m2, b2, l2 in maps[1:]:
+        bias = m2 @ bias + b2
+        mat = m2 @ mat
+        lad = lad + l2
+    spatial = x.shape[2] * x.shape[3] if x.dim() == 4 else 1
+    return ops.chanmix(x, mat, bias), (lad * spatial if spatial != 1 else lad)
+
+
+def apply_chain(transforms, x, context, inverse):
+    """Evaluate ``transforms`` in order (reversed when ``inverse``) and sum their log-dets.  Runs of
+    affine layers are merged into one launch (``config.fuse_linear_glue``; off = one launch each)."""
+    from .base import _add_lad
+
+    seq = transforms[::-1] if inverse else transforms
+    total = None
+    run = []  # pending affine maps (M, m, lad) to compose
+
+    def flush(x, total):
+        if not run:
+            return x, total
+        y, lad = apply_affine(list(run), x)
+        run.clear()
+        return y, _add_lad(total, lad)
+
+    for t in seq:
+        if _linear_capable(t, x):
+            if not inverse and getattr(t, "_needs_data_init", None) is not None and t._needs_data_init():
+                x, total = flush(x, total)  # ActNorm's data-dependent init must see its real input
+                t._initialize(x)
+            run.append(t._affine_map(inverse))
+            if not config.fuse_linear_glue:
+                x, total = flush(x, total)
+            continue
+        x, total = flush(x, total)
+        x, lad = t._apply_transform(x, context, inverse)
+        total = _add_lad(total, lad)
+    x, total = flush(x, total)
+    return x, total
+
+
+class VersionedCache:
+    """Caches tensors derived from parameters, keyed on the parameters' in-place version counters
+    (bumped by optimizer steps / load_state_dict).  Under autograd the entry is additionally bound
+    to the current model-level pass so that a freed graph is never reused."""
+
+    def __init__(self):
+        self._key = None
+        self._value = None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version) for p in params) + (torch.is_grad_enabled() and any(p.requires_grad for p in params),)
+        if key[-1]:
+            key = key + (current_pass(),)
+            if current_pass() == 0:
+                return build()
+        if key != self._key:
+            self._value = build()
+            self._key = key
+        return self._value

@@ -1,0 +1,137 @@
+"""LU-parameterised linear layer (reference: manifold_flow/transforms/lu.py, linear.py:32-132).
+
+W = L U with L unit lower triangular and U upper triangular with diagonal softplus(.) + eps
+(lu.py:44-54,118-120).  Small layers (features <= 96) are dense C x C affine maps that
+``fusion.apply_chain`` composes with their neighbours into one channel-mix launch.  Large layers
+(``LULinear(3840)`` of the image post-processing, architectures/image_transforms.py:240-258) keep
+their triangles dense on the device - rebuilt once per optimizer step instead of on every call via
+host index arrays (lu.py:18-20,44-54) - and run as plain library GEMMs / triangular solves.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+from torch.nn import init
+
+from ..b200.cabi import require_cuda
+from ..utils import various
+from .base import Transform
+from .fusion import MAX_FUSED_CHANNELS, VersionedCache
+
+
+class Linear(Transform):
+    """Base of linear transforms: ``features``, ``bias`` and the (unused by default) eval cache flag
+    of the reference (linear.py:32-48)."""
+
+    def __init__(self, features, using_cache=False):
+        if not various.is_positive_int(features):
+            raise TypeError("Number of features must be a positive integer.")
+        super().__init__()
+        self.features = features
+        self.bias = nn.Parameter(torch.zeros(features))
+        self.using_cache = using_cache
+
+    def use_cache(self, mode=True):
+        if not various.is_bool(mode):
+            raise TypeError("Mode must be boolean.")
+        self.using_cache = mode  # dense factors are always cached per parameter version here
+
+
+class LULinear(Linear):
+    def __init__(self, features, using_cache=False, identity_init=True, eps=1e-3):
+        super().__init__(features, using_cache)
+        self.eps = eps
+        n_tri = ((features - 1) * features) // 2
+        self.lower_entries = nn.Parameter(torch.zeros(n_tri))
+        self.upper_entries = nn.Parameter(torch.zeros(n_tri))
+        self.unconstrained_upper_diag = nn.Parameter(torch.zeros(features))
+        # flat positions of the strictly-lower / strictly-upper entries in row-major order
+        # (np.tril_indices / np.triu_indices order, lu.py:18-19); not part of the state_dict
+        rows, cols = np.tril_indices(features, k=-1)
+        self.register_buffer("_lower_pos", torch.from_numpy(rows * features + cols), persistent=False)
+        rows, cols = np.triu_indices(features, k=1)
+        self.register_buffer("_upper_pos", torch.from_numpy(rows * features + cols), persistent=False)
+        self._dense_cache = VersionedCache()
+        self._map_cache = {False: VersionedCache(), True: VersionedCache()}
+        self._initialize(identity_init)
+
+    def _initialize(self, identity_init):
+        init.zeros_(self.bias)
+        if identity_init:  # lu.py:33-37
+            init.zeros_(self.lower_entries)
+            init.zeros_(self.upper_entries)
+            init.constant_(self.unconstrained_upper_diag, float(np.log(np.exp(1 - self.eps) - 1)))
+        else:
+            stdv = 1.0 / np.sqrt(self.features)
+            init.uniform_(self.lower_entries, -stdv, stdv)
+            init.uniform_(self.upper_entries, -stdv, stdv)
+            init.uniform_(self.unconstrained_upper_diag, -stdv, stdv)
+
+    # ---- dense factors -------------------------------------------------------------------
+    @property
+    def upper_diag(self):
+        return F.softplus(self.unconstrained_upper_diag) + self.eps
+
+    def logabsdet(self):
+        return torch.sum(torch.log(self.upper_diag))
+
+    def _lu_params(self):
+        return (self.lower_entries, self.upper_entries, self.unconstrained_upper_diag)
+
+    def _create_lower_upper(self):
+        def build():
+            n = self.features
+            eye = torch.eye(n, dtype=self.bias.dtype, device=self.bias.device)
+            lower = eye.reshape(-1).index_put((self._lower_pos,), self.lower_entries).view(n, n)
+            upper = torch.diag(self.upper_diag).reshape(-1).index_put((self._upper_pos,), self.upper_entries).view(n, n)
+            return lower, upper
+
+        return self._dense_cache.get(self._lu_params(), build)
+
+    def weight(self):
+        lower, upper = self._create_lower_upper()
+        return lower @ upper
+
+    def weight_inverse(self):
+        lower, upper = self._create_lower_upper()
+        eye = torch.eye(self.features, dtype=lower.dtype, device=lower.device)
+        inv_lower = torch.linalg.solve_triangular(lower, eye, upper=False, unitriangular=True)
+        return torch.linalg.solve_triangular(upper, inv_lower, upper=True)
+
+    # ---- fused small path ------------------------------------------------------------------
+    def _can_fuse(self, x):
+        return self.features <= MAX_FUSED_CHANNELS and x.dim() == 2
+
+    def _affine_map(self, inverse):
+        def build():
+            if not inverse:
+                return self.weight(), self.bias, self.logabsdet()
+            w_inv = self.weight_inverse()
+            return w_inv, -(w_inv @ self.bias), -self.logabsdet()
+
+        return self._map_cache[bool(inverse)].get(self._lu_params() + (self.bias,), build)
+
+    # ---- large path: library GEMMs on cached dense triangles -------------------------------
+    def _apply_transform(self, inputs, context, inverse):
+        require_cuda(inputs)
+        if inputs.dim() != 2 or inputs.shape[1] != self.features:
+            raise ValueError("Expected inputs of shape [N, {}], got {}".format(self.features, tuple(inputs.shape)))
+        if self._can_fuse(inputs):
+            from .fusion import apply_affine
+
+            return apply_affine([self._affine_map(inverse)], inputs)
+        lower, upper = self._create_lower_upper()
+        if not inverse:  # lu.py:56-73
+            outputs = F.linear(F.linear(inputs, upper), lower, self.bias)
+            return outputs, self.logabsdet()
+        outputs = (inputs - self.bias).t()  # lu.py:75-95
+        outputs = torch.linalg.solve_triangular(lower, outputs, upper=False, unitriangular=True)
+        outputs = torch.linalg.solve_triangular(upper, outputs, upper=True)
+        return outputs.t(), -self.logabsdet()
+
+    # reference spelling of the two directions
+    def forward_no_cache(self, inputs, full_jacobian=False):
+        return self.forward(inputs, full_jacobian=full_jacobian)
+
+    def inverse_no_cache(self, inputs, full_jacobian=False):
+        return self.inverse(inputs, full_jacobian=full_jacobian)

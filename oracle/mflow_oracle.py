@@ -523,8 +523,8 @@ def mflow_forward(
     # _decode :104-122
     h_dec, inv_ld_inner = apply(model["inner"], sd, "inner_transform.", u, context, True)
     h_full = torch.cat((h_dec, h_dec.new_zeros(b, h.shape[1] - n)), dim=1)  # projections.py:37-47
-    if len(model["data_shape"]) == 3:
-        h_full = h_full.view(b, *model["data_shape"])
+    # ManifoldFlow builds ProjectionSplit from the *total* dims (ints), so it stays in "vector" mode
+    # and the flat [B, D] tensor goes straight into outer_transform.inverse (manifold_flow.py:30)
     x_reco, inv_ld_outer = apply(model["outer"], sd, "outer_transform.", h_full, octx, True)
     # _log_prob :124-157
     if mode in ("pie", "mf-fixed-manifold"):
@@ -552,20 +552,55 @@ def batch_jacobian_wrt(outputs: Tensor, inputs: Tensor) -> Tensor:
     return torch.stack(rows, dim=1)
 
 
+def permutation_jacobian_reference(perm: Tensor, inverse: bool, batch: int, dtype) -> Tensor:
+    """The matrix Permutation._permute returns for full_jacobian=True (permutations.py:38-71):
+    ``jacobian[permutation, arange] = 1``.  NOTE: for outputs[j] = inputs[permutation[j]] the true
+    Jacobian has ones at [j, permutation[j]]; the reference's matrix is its transpose, which only
+    coincides for involutions.  ``mode="mf"`` likelihoods of the reference are computed with this
+    matrix, so parity requires reproducing it [probed: 3-cycle permutation, autograd vs reference]."""
+    idx = torch.argsort(perm) if inverse else perm
+    n = perm.numel()
+    jac = torch.zeros(n, n, dtype=dtype)
+    jac[idx, torch.arange(n)] = 1.0
+    return jac.unsqueeze(0).expand(batch, -1, -1)
+
+
+def apply_with_jacobian(spec, sd: StateDict, p: str, x: Tensor, context: Optional[Tensor], inverse: bool):
+    """(outputs, jacobian[B, D, D]) the way CompositeTransform._cascade(full_jacobian=True) builds it
+    (base.py:52-69): per-layer Jacobians multiplied left to right.  Leaf layers: autograd Jacobian of
+    the layer (what CouplingTransform does via batch_jacobian, coupling.py:71-105,141-170, and what
+    LULinear states analytically, lu.py:69-71,89-91); permutations: the reference's own matrix."""
+    kind = spec[0]
+    if kind == "composite":
+        children = list(enumerate(spec[1]))
+        total = None
+        for i, child in (reversed(children) if inverse else children):
+            x, jac = apply_with_jacobian(child, sd, f"{p}_transforms.{i}.", x, context, inverse)
+            total = jac if total is None else torch.bmm(jac, total)
+        return x, total
+    if kind == "perm":
+        perm = sd[p + "_permutation"]
+        return permute(x, perm, inverse), permutation_jacobian_reference(perm, inverse, x.shape[0], x.dtype)
+    xin = x.detach().requires_grad_(True)
+    y, _ = apply(spec, sd, p, xin, context, inverse)
+    return y.detach(), batch_jacobian_wrt(y, xin)
+
+
 def mflow_log_prob_mf(model: dict, sd: StateDict, x: Tensor, context: Optional[Tensor] = None):
     """mode="mf" exactly as the reference composes it (manifold_flow.py:115-120,140-147):
-    J = d outer^{-1}(h) / dh restricted to the first n columns, log p = log N(u) -
-    1/2 log det(J^T J) - inv_log_det_inner.  Returns (x_reco, log_prob, u)."""
+    J = chain of per-layer Jacobians of outer^{-1} restricted to the first n columns,
+    log p = log N(u) - 1/2 log det(J^T J) - inv_log_det_inner.  Returns (x_reco, log_prob, u)."""
     n = model["latent_dim"]
     octx = context if model.get("conditional_outer", False) else None
     b = x.shape[0]
-    h, _ = apply(model["outer"], sd, "outer_transform.", x, octx, False)
-    h = h.reshape(b, -1)
-    u, _ = apply(model["inner"], sd, "inner_transform.", h[:, :n], context, False)
-    h_dec, inv_ld_inner = apply(model["inner"], sd, "inner_transform.", u, context, True)
-    h_full = torch.cat((h_dec, h_dec.new_zeros(b, h.shape[1] - n)), dim=1).detach().requires_grad_(True)
-    x_reco, _ = apply(model["outer"], sd, "outer_transform.", h_full, octx, True)
-    jac = batch_jacobian_wrt(x_reco.reshape(b, -1), h_full)[:, :, :n]
+    with torch.no_grad():
+        h, _ = apply(model["outer"], sd, "outer_transform.", x, octx, False)
+        h = h.reshape(b, -1)
+        u, _ = apply(model["inner"], sd, "inner_transform.", h[:, :n], context, False)
+        h_dec, inv_ld_inner = apply(model["inner"], sd, "inner_transform.", u, context, True)
+        h_full = torch.cat((h_dec, h_dec.new_zeros(b, h.shape[1] - n)), dim=1)
+    x_reco, jac = apply_with_jacobian(model["outer"], sd, "outer_transform.", h_full, octx, True)
+    jac = jac[:, :, :n]
     jtj = torch.bmm(jac.transpose(-2, -1), jac)
     log_prob = standard_normal_log_prob(u) - 0.5 * torch.slogdet(jtj)[1] - inv_ld_inner
     return x_reco.detach(), log_prob.detach(), u.detach()

@@ -1,0 +1,173 @@
+"""GPU parity of single transforms (couplings, ActNorm, 1x1 conv, LU, permutations, squeeze, LogTanh,
+partial post-processing) against the golden vectors frozen from the reference, both directions, plus
+gradients against the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+import golden_util as gu
+import mflow_oracle as oracle
+from test_oracle_golden import _layer_spec
+
+pytestmark = pytest.mark.gpu
+
+L = gu.load_npz("layers.npz")
+CASES = [str(c) for c in L["cases"] if not str(c).startswith("actnorm_init")]
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def build_layer(name):
+    from manifold_flow import nn as nn_, transforms
+    from manifold_flow.utils import various
+
+    parts = name.split("_")
+    if name.startswith("vcoup"):
+        d, k, t, cf, even = int(parts[1][1:]), int(parts[2][1:]), float(parts[3][1:]), int(parts[4][3:]) or None, parts[5] == "even"
+        net = lambda i, o: nn_.ResidualNet(i, o, hidden_features=16, context_features=cf, num_blocks=2)
+        return transforms.PiecewiseRationalQuadraticCouplingTransform(
+            mask=various.create_alternating_binary_mask(d, even=even), transform_net_create_fn=net, num_bins=k, tails="linear", tail_bound=t)
+    if name.startswith("icoup"):
+        c, cf, hidden = int(parts[1][1:]), int(parts[3][3:]) or None, int(parts[4][1:])
+        net = lambda i, o: nn_.ConvResidualNet(i, o, hidden_channels=hidden, context_channels=cf, num_blocks=2)
+        return transforms.PiecewiseRationalQuadraticCouplingTransform(
+            mask=various.create_mid_split_binary_mask(c), transform_net_create_fn=net, num_bins=11, tails="linear", tail_bound=10.0)
+    if name == "partial_mlp":
+        mask = various.create_mlt_channel_mask(3 * 8 * 8, channels_per_level=2 * np.array([1, 2]), resolution=8)
+        pdim = int(mask.sum())
+        return transforms.CompositeTransform([
+            transforms.PartialTransform(mask, transforms.CompositeTransform([transforms.LULinear(pdim), transforms.LogTanh(cut_point=1), transforms.LULinear(pdim)])),
+            transforms.MaskBasedPermutation(mask)])
+    return {
+        "actnorm_vec": lambda: transforms.ActNorm(14), "actnorm_img": lambda: transforms.ActNorm(12),
+        "conv1x1_C12": lambda: transforms.OneByOneConvolution(12), "conv1x1_C96": lambda: transforms.OneByOneConvolution(96),
+        "lu_D14": lambda: transforms.LULinear(14), "lu_D40": lambda: transforms.LULinear(40),
+        "perm_D40": lambda: transforms.RandomPermutation(40), "squeeze": lambda: transforms.SqueezeTransform(),
+        "affine_scalar": lambda: transforms.AffineScalarTransform(scale=1.0 / 256, shift=-0.5),
+        "logtanh": lambda: transforms.LogTanh(cut_point=1),
+    }[name]()
+
+
+def load_case(name, device):
+    from manifold_flow import transforms
+
+    layer = build_layer(name)
+    sd = {k.split("/sd/")[1]: _t(v) for k, v in L.items() if k.startswith(name + "/sd/")}
+    layer.load_state_dict(sd)
+    for m in layer.modules():
+        if isinstance(m, transforms.ActNorm):
+            m.initialized = True
+    layer.eval().to(device)
+    x = _t(L[f"{name}/x"])
+    ctx = _t(L[f"{name}/ctx"]) if f"{name}/ctx" in L else None
+    return layer, sd, x, ctx
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_layer_forward_inverse_match_reference(cuda_device, name):
+    layer, sd, x, ctx = load_case(name, cuda_device)
+    cd = None if ctx is None else ctx.to(cuda_device)
+    with torch.no_grad():
+        y, lad = layer(x.to(cuda_device), context=cd)
+        xi, ladi = layer.inverse(_t(L[f"{name}/y"]).to(cuda_device), context=cd)
+    scale = max(1.0, float(_t(L[f"{name}/y"]).abs().max()))
+    torch.testing.assert_close(y.cpu(), _t(L[f"{name}/y"]), rtol=1e-5, atol=1e-5 * scale)
+    torch.testing.assert_close(lad.cpu(), _t(L[f"{name}/lad"]), rtol=1e-5, atol=1e-4)
+    scale = max(1.0, float(x.abs().max()))
+    torch.testing.assert_close(xi.cpu(), _t(L[f"{name}/xi"]), rtol=1e-5, atol=2e-5 * scale)
+    torch.testing.assert_close(ladi.cpu(), _t(L[f"{name}/ladi"]), rtol=1e-5, atol=1e-4)
+    assert lad.shape == (x.shape[0],) and ladi.shape == (x.shape[0],)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_layer_gradients_match_oracle(cuda_device, name, inverse):
+    layer, sd, x, ctx = load_case(name, cuda_device)
+    if inverse:
+        x = _t(L[f"{name}/y"])
+    g = torch.Generator().manual_seed(11)
+    spec = _layer_spec(name)
+    # oracle in float64 with autograd
+    sdo = {k: (v.double().requires_grad_(True) if torch.is_floating_point(v) and k.split(".")[-1] not in ("_shift", "_scale") else
+               (v.double() if torch.is_floating_point(v) else v)) for k, v in sd.items()}
+    xo = x.double().requires_grad_(True)
+    co = None if ctx is None else ctx.double()
+    yo, lado = oracle.apply(spec, sdo, "", xo, co, inverse)
+    gy = torch.randn(yo.shape, generator=g)
+    gl = torch.randn(lado.shape, generator=g)
+    ((yo * gy.double()).sum() + (lado * gl.double()).sum()).backward()
+    # product on the GPU
+    xd = x.to(cuda_device).requires_grad_(True)
+    cd = None if ctx is None else ctx.to(cuda_device)
+    y, lad = layer.inverse(xd, context=cd) if inverse else layer(xd, context=cd)
+    ((y * gy.to(cuda_device)).sum() + (lad * gl.to(cuda_device)).sum()).backward()
+    torch.testing.assert_close(xd.grad.cpu().double(), xo.grad, rtol=2e-4, atol=2e-4)
+    for k, p in layer.named_parameters():
+        ref = sdo[k].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        scale = max(1.0, float(ref.abs().max()))
+        torch.testing.assert_close(p.grad.cpu().double(), ref, rtol=5e-4, atol=5e-5 * scale, msg=lambda m: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("name", ["actnorm_init_vec", "actnorm_init_img"])
+def test_actnorm_data_dependent_init(cuda_device, name):
+    from manifold_flow import transforms
+
+    x = _t(L[f"{name}/x"])
+    layer = transforms.ActNorm(x.shape[1]).to(cuda_device)
+    layer.train()
+    y, lad = layer(x.to(cuda_device))
+    assert layer.initialized
+    torch.testing.assert_close(layer.log_scale.detach().cpu(), _t(L[f"{name}/log_scale"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(layer.shift.detach().cpu(), _t(L[f"{name}/shift"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(y.detach().cpu(), _t(L[f"{name}/y"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lad.detach().cpu(), _t(L[f"{name}/lad"]), rtol=1e-5, atol=1e-5)
+
+
+def test_fused_step_equals_unfused(cuda_device):
+    """ActNorm + 1x1 conv composed into one channel-mix launch gives the same numbers as the layers
+    applied one by one (and as the oracle)."""
+    from manifold_flow import transforms
+    from manifold_flow.b200 import config
+
+    torch.manual_seed(5)
+    act, conv = transforms.ActNorm(24), transforms.OneByOneConvolution(24)
+    comp = transforms.CompositeTransform([act, conv]).to(cuda_device).eval()
+    sd = gu.perturb_state_dict(comp.state_dict(), seed=3)
+    comp.load_state_dict(sd)
+    act.initialized = True
+    x = torch.randn(4, 24, 8, 8)
+    with torch.no_grad():
+        y_f, lad_f = comp(x.to(cuda_device))
+        config.fuse_linear_glue = False
+        try:
+            y_u, lad_u = comp(x.to(cuda_device))  # one launch per layer
+        finally:
+            config.fuse_linear_glue = True
+        xi, ladi = comp.inverse(y_f)
+    torch.testing.assert_close(y_f, y_u, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lad_f, lad_u, rtol=1e-6, atol=1e-5)
+    sdc = {k: v.cpu() for k, v in sd.items()}
+    ref_y, ref_l = oracle.apply(("composite", [("actnorm",), ("conv1x1",)]), sdc, "", x, None, False)
+    torch.testing.assert_close(y_f.cpu(), ref_y, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lad_f.cpu(), ref_l, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(xi.cpu(), x, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close((lad_f + ladi).cpu(), torch.zeros(4), rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("d,n", [(3, 2), (40, 14), (64, 32), (5, 5)])
+def test_jtj_logdet_vs_slogdet_fp64(cuda_device, d, n):
+    from manifold_flow.b200 import ops
+
+    g = torch.Generator().manual_seed(d * n)
+    jac = torch.randn(37, d, n, generator=g)
+    jac[3] *= 1e-3  # badly scaled
+    jac[4, :, 0] = jac[4, :, 1] * (1 + 1e-3)  # nearly rank deficient (cond(J^T J) ~ 1e7)
+    ref = torch.slogdet(torch.bmm(jac.double().transpose(1, 2), jac.double()))[1]
+    got = ops.jtj_logdet(jac.to(cuda_device)).cpu().double()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)

@@ -1,0 +1,249 @@
+"""GPU parity of kernel (a), through the C ABI: fused RQ-spline forward / inverse / backward in both
+data layouts against the golden vectors frozen from the reference and against the oracle.
+
+Tolerances (BASELINE.json:north_star): bin indices bit-exact on given knots; outputs and logabsdet
+within 1e-5 relative (+1e-5 absolute floor for values near zero) in fp32; tails exact identity."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import mflow_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+S = gu.load_npz("spline.npz")
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _t(a, dev=None):
+    t = torch.from_numpy(np.asarray(a))
+    return t if dev is None else t.to(dev)
+
+
+@pytest.mark.parametrize("t", [3, 10])
+def test_search_bitexact_on_given_knots(cuda_device, t):
+    from manifold_flow.b200 import ops
+
+    knots, v, bins = (_t(S[f"search_T{t}/{k}"]) for k in ("knots", "values", "bins"))
+    kk = knots[:, None, :].expand(-1, v.shape[1], -1).reshape(-1, knots.shape[1]).contiguous()
+    got = ops.rqs_search(kk.to(cuda_device), v.reshape(-1).to(cuda_device)).cpu().view(bins.shape)
+    assert torch.equal(got.long(), bins)
+
+
+@pytest.mark.parametrize("name", [str(c) for c in S["cases"]])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_function_matches_golden(cuda_device, name, inverse):
+    from manifold_flow.transforms.splines import unconstrained_rational_quadratic_spline as spline
+
+    t = float(name.split("_")[1][1:])
+    tag = "inv" if inverse else "fwd"
+    x, w, h, d = (_t(S[f"{name}/{k}"], cuda_device) for k in "xwhd")
+    y, lad = spline(x, w, h, d, inverse=inverse, tails="linear", tail_bound=t)
+    y, lad = y.cpu(), lad.cpu()
+    xc = x.cpu()
+    for ref_y, ref_l in ((S[f"{name}/{tag}_y"], S[f"{name}/{tag}_lad"]), (S[f"{name}/{tag}_y64"].astype(np.float32), S[f"{name}/{tag}_lad64"].astype(np.float32))):
+        torch.testing.assert_close(y, _t(ref_y), rtol=RTOL, atol=ATOL * max(1.0, t / 3))
+        # saturated softmaxes put |logabsdet| at ~7; relative tolerance covers them
+        torch.testing.assert_close(lad, _t(ref_l), rtol=2e-5, atol=5e-5)
+    out = (xc < -t) | (xc > t)
+    assert out.any()
+    assert torch.equal(y[out], xc[out]) and torch.all(lad[out] == 0)
+
+
+@pytest.mark.parametrize("k,t", [(8, 3.0), (10, 6.0), (11, 10.0), (4, 1.0), (16, 5.0)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_rows_layout_vs_oracle_large(cuda_device, k, t, inverse):
+    from manifold_flow.b200 import ops
+
+    g = torch.Generator().manual_seed(5 + k)
+    n = 40013  # ragged: not a multiple of any tile size
+    x = torch.randn(n, generator=g) * (t / 2)
+    params = torch.randn(n, 3 * k - 1, generator=g) * 1.5
+    ref_y, ref_l, ref_b = oracle.rqs(x.double(), params[:, :k].double(), params[:, k : 2 * k].double(), params[:, 2 * k :].double(), inverse, t,
+                                     return_bins=True)
+    y, lad, bins = ops.rqs_elementwise(x.to(cuda_device), params.to(cuda_device), k, t, inverse=inverse, return_bins=True)
+    torch.testing.assert_close(y.cpu().double(), ref_y, rtol=RTOL, atol=ATOL * max(1.0, t / 3))
+    torch.testing.assert_close(lad.cpu().double(), ref_l, rtol=2e-5, atol=5e-5)
+    # end-to-end bins: a flip is only legal within a couple of ulps of a knot
+    mism = (bins.cpu().long() != ref_b).sum().item()
+    assert mism <= max(2, n // 20000), f"{mism} bin mismatches out of {n}"
+
+
+def _plane_case(k, t, b, c, hh, ww, seed):
+    g = torch.Generator().manual_seed(seed)
+    ct = (c + 1) // 2
+    x = torch.randn(b, c, hh, ww, generator=g) * (t / 2)
+    params = torch.randn(b, ct * (3 * k - 1), hh, ww, generator=g) * 8.0
+    return x, params, ct
+
+
+def _oracle_planes(x, params, ct, k, t, hidden, inverse):
+    b, c, hh, ww = x.shape
+    p = params.reshape(b, ct, -1, hh, ww).permute(0, 1, 3, 4, 2)
+    scale = np.sqrt(hidden)
+    y_t, lad = oracle.rqs(x[:, :ct], p[..., :k] / scale, p[..., k : 2 * k] / scale, p[..., 2 * k :], inverse, t)
+    out = x.clone()
+    out[:, :ct] = y_t
+    return out, oracle.sum_except_batch(lad)
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 32, 32), (2, 24, 16, 16), (5, 48, 8, 8), (7, 96, 4, 4), (2, 6, 5, 3), (1, 2, 1, 1)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_coupling_planes_layout_vs_oracle(cuda_device, shape, inverse):
+    from manifold_flow.b200 import ops
+
+    k, t, hidden = 11, 10.0, 100
+    b, c, hh, ww = shape
+    x, params, ct = _plane_case(k, t, b, c, hh, ww, seed=b * 100 + c)
+    geom = ops.SplineGeometry(ct, 0, 1, c - ct, ct, 1)
+    y, lad = ops.rqs_coupling(x.to(cuda_device), params.to(cuda_device), geom, k, t, 1e-3, 1e-3, 1e-3, np.sqrt(hidden), inverse)
+    ref_y, ref_l = _oracle_planes(x.double(), params.double(), ct, k, t, hidden, inverse)
+    torch.testing.assert_close(y.cpu().double(), ref_y, rtol=RTOL, atol=ATOL * t / 3)
+    torch.testing.assert_close(lad.cpu().double(), ref_l, rtol=1e-5, atol=1e-4 * max(1.0, ct * hh * ww / 1000))
+    # identity channels are copied bit-exactly
+    assert torch.equal(y.cpu()[:, ct:], x[:, ct:])
+    # fp32 oracle (what the reference computes on CPU) must agree as well
+    ref32_y, ref32_l = _oracle_planes(x, params, ct, k, t, hidden, inverse)
+    torch.testing.assert_close(y.cpu(), ref32_y, rtol=RTOL, atol=ATOL * t / 3)
+
+
+def test_per_sample_logdet_is_deterministic(cuda_device):
+    from manifold_flow.b200 import ops
+
+    k, t = 11, 10.0
+    x, params, ct = _plane_case(k, t, 25, 12, 32, 32, seed=3)
+    geom = ops.SplineGeometry(ct, 0, 1, 12 - ct, ct, 1)
+    xs, ps = x.to(cuda_device), params.to(cuda_device)
+    first = ops.rqs_coupling(xs, ps, geom, k, t, 1e-3, 1e-3, 1e-3, 10.0, False)[1]
+    for _ in range(5):
+        again = ops.rqs_coupling(xs, ps, geom, k, t, 1e-3, 1e-3, 1e-3, 10.0, False)[1]
+        assert torch.equal(first, again)
+
+
+@pytest.mark.parametrize("k,t", [(8, 3.0), (11, 10.0)])
+def test_round_trip_and_cancelling_logdets(cuda_device, k, t):
+    from manifold_flow.b200 import ops
+
+    g = torch.Generator().manual_seed(k)
+    n = 1 << 16
+    x = (torch.randn(n, generator=g) * (t / 2)).to(cuda_device)
+    params = torch.randn(n, 3 * k - 1, generator=g).to(cuda_device)
+    y, lad = ops.rqs_elementwise(x, params, k, t)
+    xi, ladi = ops.rqs_elementwise(y, params, k, t, inverse=True)
+    assert (xi - x).abs().max().item() <= 2e-5 * max(1.0, t / 3)
+    assert (lad + ladi).abs().max().item() <= 5e-5
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("layout", ["rows", "planes"])
+def test_backward_matches_oracle_autograd(cuda_device, inverse, layout):
+    from manifold_flow.b200 import ops
+
+    k, t, hidden = 11, 10.0, 100.0
+    g = torch.Generator().manual_seed(17)
+    if layout == "rows":
+        b, d = 301, 14
+        ct = 7
+        x = torch.randn(b, d, generator=g) * (t / 2)
+        params = torch.randn(b, ct * (3 * k - 1), generator=g) * 6
+        geom = ops.SplineGeometry(ct, 0, 2, d - ct, 1, 2)  # even features transformed
+        tr, idn = slice(0, None, 2), slice(1, None, 2)
+    else:
+        b, c, hh, ww = 3, 12, 8, 8
+        ct = 6
+        x = torch.randn(b, c, hh, ww, generator=g) * (t / 2)
+        params = torch.randn(b, ct * (3 * k - 1), hh, ww, generator=g) * 6
+        geom = ops.SplineGeometry(ct, 0, 1, c - ct, ct, 1)
+        tr, idn = slice(0, ct), slice(ct, None)
+    gy = torch.randn(x.shape, generator=g)
+    gl = torch.randn(b, generator=g)
+
+    xd = x.to(cuda_device).requires_grad_(True)
+    pd = params.to(cuda_device).requires_grad_(True)
+    y, lad = ops.rqs_coupling(xd, pd, geom, k, t, 1e-3, 1e-3, 1e-3, np.sqrt(hidden), inverse)
+    ((y * gy.to(cuda_device)).sum() + (lad * gl.to(cuda_device)).sum()).backward()
+
+    xo = x.double().requires_grad_(True)
+    po = params.double().requires_grad_(True)
+    if layout == "rows":
+        pv = po.reshape(b, ct, -1)
+    else:
+        pv = po.reshape(b, ct, -1, hh, ww).permute(0, 1, 3, 4, 2)
+    scale = np.sqrt(hidden)
+    y_t, lad_o = oracle.rqs(xo[:, tr], pv[..., :k] / scale, pv[..., k : 2 * k] / scale, pv[..., 2 * k :], inverse, t)
+    loss = (y_t * gy.double()[:, tr]).sum() + (xo[:, idn] * gy.double()[:, idn]).sum() + (oracle.sum_except_batch(lad_o) * gl.double()).sum()
+    loss.backward()
+    torch.testing.assert_close(xd.grad.cpu().double(), xo.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(pd.grad.cpu().double(), po.grad, rtol=1e-4, atol=2e-5)
+
+
+def test_elementwise_backward_matches_oracle(cuda_device):
+    from manifold_flow.transforms.splines import unconstrained_rational_quadratic_spline as spline
+
+    k, t = 8, 3.0
+    g = torch.Generator().manual_seed(23)
+    n = 777
+    x = torch.randn(n, generator=g) * 1.5
+    w, h, d = torch.randn(n, k, generator=g), torch.randn(n, k, generator=g), torch.randn(n, k - 1, generator=g)
+    gy, gl = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    for inverse in (False, True):
+        leaves = [v.to(cuda_device).requires_grad_(True) for v in (x, w, h, d)]
+        y, lad = spline(*leaves, inverse=inverse, tails="linear", tail_bound=t)
+        ((y * gy.to(cuda_device)).sum() + (lad * gl.to(cuda_device)).sum()).backward()
+        ref = [v.double().requires_grad_(True) for v in (x, w, h, d)]
+        yo, lo = oracle.rqs(*ref, inverse, t)
+        ((yo * gy.double()).sum() + (lo * gl.double()).sum()).backward()
+        for a, b_ in zip(leaves, ref):
+            torch.testing.assert_close(a.grad.cpu().double(), b_.grad, rtol=1e-4, atol=2e-5)
+
+
+def test_edge_cases(cuda_device):
+    from manifold_flow.b200 import ops
+
+    k, t = 8, 3.0
+    # empty batch
+    y, lad = ops.rqs_elementwise(torch.empty(0, device=cuda_device), torch.empty(0, 3 * k - 1, device=cuda_device), k, t)
+    assert y.numel() == 0 and lad.numel() == 0
+    # everything in the tails, NaN passes through like the reference's mask logic
+    x = torch.tensor([-5.0, 4.0, float("inf"), float("nan")], device=cuda_device)
+    y, lad = ops.rqs_elementwise(x, torch.zeros(4, 3 * k - 1, device=cuda_device), k, t)
+    assert torch.equal(y[:3], x[:3]) and torch.isnan(y[3]) and torch.all(lad == 0)
+    # zero parameters are the identity map inside the box too (identity-initialised flow)
+    x = torch.linspace(-t, t, 1001, device=cuda_device)
+    y, lad = ops.rqs_elementwise(x, torch.zeros(1001, 3 * k - 1, device=cuda_device), k, t)
+    assert (y - x).abs().max().item() < 2e-6 and lad.abs().max().item() < 2e-6
+    # unsupported bin count fails loudly
+    with pytest.raises(ValueError):
+        ops.rqs_elementwise(x, torch.zeros(1001, 3 * 7 - 1, device=cuda_device), 7, t)
+    # too many bins for the minimal width (reference: ValueError, rational_quadratic.py:97-100)
+    with pytest.raises(ValueError):
+        ops.rqs_elementwise(x, torch.zeros(1001, 3 * 16 - 1, device=cuda_device), 16, t, min_w=0.1)
+
+
+def test_large_batch_rows_and_planes(cuda_device):
+    """Sizes of the spline micro-benchmark: 2^20 vector samples; 256 images."""
+    from manifold_flow.b200 import ops
+
+    k, t = 11, 10.0
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    n = 1 << 20
+    x = torch.randn(n, 2, device=cuda_device, generator=g) * 5
+    params = torch.randn(n, 32, device=cuda_device, generator=g)
+    geom = ops.SplineGeometry(1, 0, 2, 1, 1, 2)
+    y, lad = ops.rqs_coupling(x, params, geom, k, t, 1e-3, 1e-3, 1e-3, 10.0, False)
+    xi, ladi = ops.rqs_coupling(y, params, geom, k, t, 1e-3, 1e-3, 1e-3, 10.0, True)
+    assert (xi - x).abs().max().item() < 1e-4 and (lad + ladi).abs().max().item() < 1e-4
+    assert torch.equal(y[:, 1], x[:, 1])
+    # sortedness: the spline is monotone, so it preserves the order of inputs that share parameters
+    xs = torch.sort(torch.randn(4096, device=cuda_device) * 5)[0]
+    ys, _ = ops.rqs_elementwise(xs, params[:1].expand(4096, -1).contiguous(), k, t)
+    assert torch.all(ys[1:] >= ys[:-1])
+    b = 256
+    xi4 = torch.randn(b, 12, 32, 32, device=cuda_device, generator=g) * 5
+    p4 = torch.randn(b, 6 * 32, 32, 32, device=cuda_device, generator=g)
+    geom4 = ops.SplineGeometry(6, 0, 1, 6, 6, 1)
+    y4, lad4 = ops.rqs_coupling(xi4, p4, geom4, k, t, 1e-3, 1e-3, 1e-3, 10.0, False)
+    x4, ladi4 = ops.rqs_coupling(y4, p4, geom4, k, t, 1e-3, 1e-3, 1e-3, 10.0, True)
+    assert (x4 - xi4).abs().max().item() < 1e-4
+    assert (lad4 + ladi4).abs().max().item() < 2e-2  # 6144 elements per sample
