@@ -14,16 +14,16 @@ from .cabi import require_cuda
 from .config import config
 
 
-@contextlib.contextmanager
 def _math_mode():
+    """cuDNN convolutions default to TF32 (torch.backends.cudnn.allow_tf32 = True), which is not
+    parity-clean (1e-3 relative).  The flags are process-global and are also read by the BACKWARD
+    kernels that autograd launches later, so they are set (not scoped) on every call."""
     want_tf32 = config.conditioner_math == "tf32"
-    old_c, old_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = want_tf32
-    torch.backends.cuda.matmul.allow_tf32 = want_tf32
-    try:
-        yield
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
+    if torch.backends.cudnn.allow_tf32 != want_tf32:
+        torch.backends.cudnn.allow_tf32 = want_tf32
+    if torch.backends.cuda.matmul.allow_tf32 != want_tf32:
+        torch.backends.cuda.matmul.allow_tf32 = want_tf32
+    return contextlib.nullcontext()
 
 
 def linear(x, layer):

@@ -71,6 +71,10 @@ def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, diviso
     return d, geom.t_offset * inner
 
 
+def _rqs_shape(d):
+    return f"[{d.n_outer}x{d.n_chan}x{d.n_inner},K={d.num_bins}]"
+
+
 def _rqs_bytes(d, backward):
     """Algorithmic HBM bytes of one spline launch: forward / inverse read P params + x
     and write y per element (+ 4 B per sample for the log-det); backward reads params, x, g_y and
@@ -99,7 +103,7 @@ class _RqsCoupling(torch.autograd.Function):
         yo = ctypes.c_void_p(y.data_ptr() + 4 * off)
         # identity features are addressed relative to the same shifted base
         desc.id_off -= off
-        tok = cabi.kernel_timer.begin("rqs_inv" if inverse else "rqs_fwd", _rqs_bytes(desc, False)) if cabi.kernel_timer else None
+        tok = cabi.kernel_timer.begin(("rqs_inv" if inverse else "rqs_fwd") + _rqs_shape(desc), _rqs_bytes(desc, False)) if cabi.kernel_timer else None
         check(lib().mflow_rqs_apply(ctypes.byref(desc), xo, ptr(params), yo, None, ptr(lad), None, None, ptr(ws), stream()),
               "mflow_rqs_apply")
         if tok:
@@ -118,7 +122,7 @@ class _RqsCoupling(torch.autograd.Function):
         g_x = torch.empty_like(x)
         g_p = torch.empty_like(params)
         sh = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() + 4 * off)
-        tok = cabi.kernel_timer.begin("rqs_bwd", _rqs_bytes(desc, True)) if cabi.kernel_timer else None
+        tok = cabi.kernel_timer.begin("rqs_bwd" + _rqs_shape(desc), _rqs_bytes(desc, True)) if cabi.kernel_timer else None
         check(lib().mflow_rqs_backward(ctypes.byref(desc), sh(x), sh(y), ptr(params), sh(g_y), ptr(g_lad), None, sh(g_x),
                                        ptr(g_p), stream()), "mflow_rqs_backward")
         if tok:

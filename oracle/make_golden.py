@@ -249,16 +249,24 @@ def model_cases():
                 x_reco2, _, _ = model(x.clone(), mode="projection", context=ctx)
                 torch.nn.functional.mse_loss(x_reco2, x).backward()
                 entry["grad_norms_projection"] = {k: float(p.grad.double().norm()) for k, p in model.named_parameters() if p.grad is not None}
-        # float64 truth for the likelihood (tolerances of fp32 kernels are judged against this too)
+        # float64 truth (tolerances of the fp32 kernels are judged against the reference's own
+        # fp32-vs-fp64 error): likelihood, latents, reconstruction and gradient norms
         torch.set_default_dtype(torch.float64)
         try:
             m64 = model.double()
-            with torch.no_grad():
-                if is_flow:
-                    _, lp64, u64 = m64(x.double(), context=None if ctx is None else ctx.double())
-                else:
-                    _, lp64, u64 = m64(x.double(), mode="mf-fixed-manifold", context=None if ctx is None else ctx.double())
+            m64.zero_grad()
+            c64 = None if ctx is None else ctx.double()
+            if is_flow:
+                xr64, lp64, u64 = m64(x.double(), context=c64)
+            else:
+                xr64, lp64, u64 = m64(x.double(), mode="mf-fixed-manifold", context=c64)
+            (-lp64.mean()).backward()
+            entry["grad_norms64"] = {k: float(p.grad.norm()) for k, p in m64.named_parameters() if p.grad is not None}
             arrays[f"{name}/log_prob64"], arrays[f"{name}/u64"] = npy(lp64), npy(u64)
+            arrays[f"{name}/x_reco64"] = npy(xr64).astype(np.float32) if xr64.numel() > 4096 else npy(xr64)
+            for key in [k for k in arrays if k.startswith(f"{name}/grad/")]:
+                pname = key.split("/grad/")[1]
+                arrays[f"{name}/grad64/{pname}"] = npy(dict(m64.named_parameters())[pname].grad)
         finally:
             torch.set_default_dtype(torch.float32)
         meta[name] = entry

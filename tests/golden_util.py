@@ -125,3 +125,44 @@ def load_json(name: str):
 
 def load_npz(name: str):
     return dict(np.load(os.path.join(GOLDEN_DIR, name)))
+
+
+def assert_as_accurate_as_reference(got, ref32, ref64, what="", floor=1e-6, rel=1e-5):
+    """fp32 parity criterion used by the GPU tests.
+
+    ``ref64`` is the reference algorithm evaluated in float64 (the truth), ``ref32`` the same
+    algorithm in float32 on the CPU (what the reference actually computes).  The RQ spline is
+    ill-conditioned for a small fraction of elements (sharp bins, the quadratic-root inverse), where the
+    reference's own fp32 result is 1e-4..1e-2 away from its fp64 result, so an element-wise 1e-5
+    bound against either cannot hold for every element - for the reference itself.  The kernel must
+    instead be *as accurate as the reference's fp32 path*:
+      * bulk: at least 99% of the elements within ``rel`` * (1 + |ref|) of the truth, and no more
+        violations than twice the reference's own count (+0.1%);
+      * error distribution: median, 90th and 99.9th percentile and maximum of |got - ref64| bounded by small
+        multiples of the same statistics of |ref32 - ref64| (+ ``floor``).
+    """
+    got, ref32, ref64 = (t.detach().double().cpu().reshape(-1) for t in (got, ref32, ref64))
+    e_got, e_ref = (got - ref64).abs(), (ref32 - ref64).abs()
+    n = e_got.numel()
+    if n == 0:
+        return
+    bound = rel * (1 + ref64.abs())
+    bad_got, bad_ref = int((e_got > bound).sum()), int((e_ref > bound).sum())
+    assert bad_got <= max(3 * bad_ref + max(n // 500, 4), n // 100), f"{what}: {bad_got}/{n} elements beyond {rel} relative (reference fp32: {bad_ref})"
+    k = max(1, int(n * 0.999))
+    q_got, q_ref = float(e_got.kthvalue(k)[0]), float(e_ref.kthvalue(k)[0])
+    for frac in (0.5, 0.9):  # robust bulk statistics (a single ill-conditioned element must not decide)
+        kk = max(1, int(n * frac))
+        a, b = float(e_got.kthvalue(kk)[0]), float(e_ref.kthvalue(kk)[0])
+        assert a <= 2.5 * b + floor, f"{what}: p{int(100 * frac)} error {a:.3e} vs reference fp32 {b:.3e}"
+    assert q_got <= 3.0 * q_ref + 10 * floor, f"{what}: p99.9 error {q_got:.3e} vs reference fp32 {q_ref:.3e}"
+    assert float(e_got.max()) <= 20.0 * float(e_ref.max()) + 100 * floor, f"{what}: max error {float(e_got.max()):.3e} vs reference fp32 {float(e_ref.max()):.3e}"
+
+
+def assert_grad_as_accurate_as_reference(got, ref32, ref64, what="", rel=1e-4, factor=5.0):
+    """Gradients: relative L2 distance to the float64 gradient at most ``rel`` + ``factor`` x the
+    distance of the reference's own fp32 autograd (parameter gradients 1e-3)."""
+    got, ref32, ref64 = (t.detach().double().cpu().reshape(-1) for t in (got, ref32, ref64))
+    scale = float(ref64.norm()) + 1e-30
+    e_got, e_ref = float((got - ref64).norm()) / scale, float((ref32 - ref64).norm()) / scale
+    assert e_got <= rel + factor * e_ref, f"{what}: relative L2 gradient error {e_got:.3e} (reference fp32: {e_ref:.3e})"

@@ -78,7 +78,12 @@ def test_layer_forward_inverse_match_reference(cuda_device, name):
     torch.testing.assert_close(lad.cpu(), _t(L[f"{name}/lad"]), rtol=1e-5, atol=1e-4)
     scale = max(1.0, float(x.abs().max()))
     torch.testing.assert_close(xi.cpu(), _t(L[f"{name}/xi"]), rtol=1e-5, atol=2e-5 * scale)
-    torch.testing.assert_close(ladi.cpu(), _t(L[f"{name}/ladi"]), rtol=1e-5, atol=1e-4)
+    # The inverse's logabsdet is ill-conditioned in fp32 in the reference itself: on
+    # vcoup_D64_K11_T10_ctx1_odd the reference's fp32 result is 4.4e-4 away from its own fp64 result
+    # for one element, and a 1e-6 change of the conditioner output (cuBLAS vs CPU GEMM rounding)
+    # moves it by 1e-3 [probed: tools/debug_case.py; the spline kernel alone reproduces the CPU fp32
+    # numbers of that element bit for bit].  Hence the looser bound on this one quantity.
+    torch.testing.assert_close(ladi.cpu(), _t(L[f"{name}/ladi"]), rtol=2e-4, atol=3e-3)
     assert lad.shape == (x.shape[0],) and ladi.shape == (x.shape[0],)
 
 
@@ -90,28 +95,32 @@ def test_layer_gradients_match_oracle(cuda_device, name, inverse):
         x = _t(L[f"{name}/y"])
     g = torch.Generator().manual_seed(11)
     spec = _layer_spec(name)
-    # oracle in float64 with autograd
-    sdo = {k: (v.double().requires_grad_(True) if torch.is_floating_point(v) and k.split(".")[-1] not in ("_shift", "_scale") else
-               (v.double() if torch.is_floating_point(v) else v)) for k, v in sd.items()}
-    xo = x.double().requires_grad_(True)
-    co = None if ctx is None else ctx.double()
-    yo, lado = oracle.apply(spec, sdo, "", xo, co, inverse)
-    gy = torch.randn(yo.shape, generator=g)
-    gl = torch.randn(lado.shape, generator=g)
-    ((yo * gy.double()).sum() + (lado * gl.double()).sum()).backward()
+    # oracle with autograd: float64 = truth, float32 = what the reference's autograd computes
+    def oracle_grads(dtype, gy=None, gl=None):
+        cast = lambda v: v.detach().clone().to(dtype) if torch.is_floating_point(v) else v
+        sdo = {k: (cast(v).requires_grad_(True) if torch.is_floating_point(v) and k.split(".")[-1] not in ("_shift", "_scale") else cast(v))
+               for k, v in sd.items()}
+        xo = cast(x).requires_grad_(True)
+        yo, lado = oracle.apply(spec, sdo, "", xo, None if ctx is None else cast(ctx), inverse)
+        if gy is None:
+            gy, gl = torch.randn(yo.shape, generator=g), torch.randn(lado.shape, generator=g)
+        ((yo * cast(gy)).sum() + (lado * cast(gl)).sum()).backward()
+        return xo.grad, {k: v.grad for k, v in sdo.items() if torch.is_floating_point(v) and v.requires_grad}, gy, gl
+
+    gx64, gp64, gy, gl = oracle_grads(torch.float64)
+    gx32, gp32, _, _ = oracle_grads(torch.float32, gy, gl)
     # product on the GPU
     xd = x.to(cuda_device).requires_grad_(True)
     cd = None if ctx is None else ctx.to(cuda_device)
     y, lad = layer.inverse(xd, context=cd) if inverse else layer(xd, context=cd)
     ((y * gy.to(cuda_device)).sum() + (lad * gl.to(cuda_device)).sum()).backward()
-    torch.testing.assert_close(xd.grad.cpu().double(), xo.grad, rtol=2e-4, atol=2e-4)
+    gu.assert_grad_as_accurate_as_reference(xd.grad, gx32, gx64, what="grad inputs", rel=2e-4, factor=20.0)
     for k, p in layer.named_parameters():
-        ref = sdo[k].grad
+        ref = gp64[k]
         if ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
-        scale = max(1.0, float(ref.abs().max()))
-        torch.testing.assert_close(p.grad.cpu().double(), ref, rtol=5e-4, atol=5e-5 * scale, msg=lambda m: f"{k}: {m}")
+        gu.assert_grad_as_accurate_as_reference(p.grad, gp32[k], ref, what=k, rel=2e-4, factor=20.0)
 
 
 @pytest.mark.parametrize("name", ["actnorm_init_vec", "actnorm_init_img"])
@@ -137,9 +146,10 @@ def test_fused_step_equals_unfused(cuda_device):
 
     torch.manual_seed(5)
     act, conv = transforms.ActNorm(24), transforms.OneByOneConvolution(24)
-    comp = transforms.CompositeTransform([act, conv]).to(cuda_device).eval()
-    sd = gu.perturb_state_dict(comp.state_dict(), seed=3)
+    comp = transforms.CompositeTransform([act, conv]).eval()
+    sd = gu.perturb_state_dict({k: v.clone() for k, v in comp.state_dict().items()}, seed=3)
     comp.load_state_dict(sd)
+    comp.to(cuda_device)
     act.initialized = True
     x = torch.randn(4, 24, 8, 8)
     with torch.no_grad():
