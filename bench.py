@@ -269,7 +269,9 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = cabi.launch_count
+    torch.cuda.nvtx.range_push("mflow_timed_region")  # ncu --nvtx --nvtx-include "mflow_timed_region/"
     secs, _, _, _ = timed(args.steps, host_io=False)
+    torch.cuda.nvtx.range_pop()
     launches = cabi.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     value = world * b * args.steps / secs
