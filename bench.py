@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
     ap.add_argument("--config", default="cfg4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32"], help="conditioner GEMM math (default: fp32 parity mode)")

@@ -152,6 +152,26 @@ MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const flo
                            int64_t rows, int64_t n, int32_t inverse, float cut_point, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (b) Conditioner convolutions on tcgen05 tensor cores (3xTF32: fp32-accurate).
+ * Replaces nn.Conv2d 3x3 (pad 1) / 1x1 + bias (+ pre-activation ReLU, + residual, + ReLU) of
+ * ConvResidualNet / ConvResidualBlock (manifold_flow/nn/resnet.py:75-142).
+ *   x [batch, c_in, height, width] fp32 NCHW contiguous, height == width in {4, 8, 16, 32}
+ *   w_hi / w_lo [taps, n_pad, k_pad] fp32: w[tap][co][ci] split as w = w_hi + w_lo with w_hi the TF32
+ *     truncation (low 13 mantissa bits zero), zero padded to n_pad %% 128 == 0, k_pad %% 32 == 0;
+ *     taps = 9 in (dy, dx) row-major order for kernel == 3
+ *   y [batch, c_out, height, width] = conv(relu_in ? relu(x) : x) + bias (+ residual), optional ReLU
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t batch, c_in, c_out, height, width;
+  int32_t kernel;   /* 1 or 3 */
+  int32_t relu_in;  /* apply ReLU to x on the fly */
+  int32_t relu_out; /* apply ReLU to the result */
+  int64_t n_pad, k_pad;
+} mflow_conv_desc;
+MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
+                        const float* bias, const float* residual, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Likelihood epilogues.
  * ---------------------------------------------------------------------------------- */
 /* log_prob[o] = logN(u[o,:]; 0, 1) + logN(clamp(v[o,:], +-clip); 0, eps^2) + sum of the addends.

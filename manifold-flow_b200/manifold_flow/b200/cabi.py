@@ -35,6 +35,16 @@ class RqsDesc(ctypes.Structure):
     ]
 
 
+class ConvDesc(ctypes.Structure):
+    """mflow_conv_desc"""
+
+    _fields_ = [
+        ("batch", i64), ("c_in", i64), ("c_out", i64), ("height", i64), ("width", i64),
+        ("kernel", i32), ("relu_in", i32), ("relu_out", i32),
+        ("n_pad", i64), ("k_pad", i64),
+    ]
+
+
 class MixDesc(ctypes.Structure):
     """mflow_mix_desc"""
 
@@ -53,6 +63,7 @@ _SIGNATURES = {
     "mflow_rqs_apply": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
     "mflow_rqs_backward": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
+    "mflow_conv2d_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 7),
     "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),
     "mflow_chanmix_wgrad_workspace_bytes": (i64, [ctypes.POINTER(MixDesc)]),
     "mflow_chanmix_wgrad": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 6),
