@@ -159,7 +159,9 @@ MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const flo
  *   w_hi / w_lo [taps, n_pad, k_pad] fp32: w[tap][co][ci] split as w = w_hi + w_lo with w_hi the TF32
  *     truncation (low 13 mantissa bits zero), zero padded to n_pad %% 128 == 0, k_pad %% 32 == 0;
  *     taps = 9 in (dy, dx) row-major order for kernel == 3
- *   y [batch, c_out, height, width] = conv(relu_in ? relu(x) : x) + bias (+ residual), optional ReLU
+ *   y [batch, c_out, height, width] = conv(relu_in ? relu(x) : x) + bias (+ residual), optional ReLU,
+ *     then zeroed where gate <= 0 (gate: optional tensor shaped like y - the ReLU mask of the data
+ *     gradient, which is the same convolution with the weights transposed and the taps flipped)
  * ---------------------------------------------------------------------------------- */
 typedef struct {
   int64_t batch, c_in, c_out, height, width;
@@ -169,7 +171,7 @@ typedef struct {
   int64_t n_pad, k_pad;
 } mflow_conv_desc;
 MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
-                        const float* bias, const float* residual, float* y, void* stream);
+                        const float* bias, const float* residual, const float* gate, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Likelihood epilogues.

@@ -6,18 +6,23 @@
 // as an implicit GEMM per 128-pixel tile:  D[128 pixels, N out channels] += A_tap[128, 32 ci] * B_tap[N, 32 ci]^T.
 //
 // * Activations stay in the reference's NCHW fp32 layout: no im2col, no layout conversion and no channel
-//   padding in HBM.  One TMA box {W, rows, 32 channels, images} per (tap, channel block) lands in shared
-//   memory as [channel][pixel]; the tap shift is just the TMA coordinate, and the zero padding of the
-//   convolution and of channels 100..127 is TMA's out-of-bounds fill.
+//   padding in HBM.  ONE TMA box {W + 8, rows + 2, 32 channels, images} per channel block lands in shared
+//   memory as [channel][pixel + halo]; all nine taps of the stencil are cut out of it.  (The innermost TMA
+//   coordinate must be a multiple of 16 bytes, so the halo box starts 4 pixels to the left.)  The zero
+//   padding of the convolution and of channels 100..127 is TMA's out-of-bounds fill.
 // * fp32 parity on TF32 tensor cores by the 3xTF32 split: a = a_hi + a_lo with a_hi the TF32 truncation;
 //   D += A_hi B_hi + A_lo B_hi + A_hi B_lo.  Weights are split once per optimizer step on the host side of
 //   the ABI.  Activations are handled by the CTA's four transform warps between TMA arrival and the MMA:
 //   one thread per pixel reads its 32 channels (conflict-free), applies the pre-activation ReLU, splits,
-//   and writes its 128-byte row of the K-major, 128B-swizzled UMMA operand tiles (A_hi, A_lo) - i.e. the
-//   NCHW -> [pixel][channel] transposition costs no extra pass.
+//   and stores A_hi / A_lo straight into TENSOR MEMORY (tcgen05.st, thread = TMEM lane = pixel), from
+//   where the MMA reads its A operand: the NCHW -> [pixel][channel] transposition costs no extra pass
+//   and the activation operand never touches shared memory again.
 // * Accumulator: 128 lanes x 128 columns of TMEM; epilogue tcgen05.ld 32x32b gives every thread one pixel
 //   row, so for a fixed output channel a warp stores 32 consecutive pixels (coalesced NCHW writes) with
-//   bias / residual / ReLU fused.
+//   bias / residual / ReLU / ReLU-mask fused.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 4-7 = transform, then
+//   epilogue.  Hand-offs through mbarrier rings; tcgen05.commit releases slots.  Two CTAs share an SM so
+//   that one CTA's prologue / epilogue overlaps the other's main loop.
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -29,25 +34,33 @@ namespace mflow {
 using namespace ptx;
 
 constexpr int kTileM = 128;   // pixels per CTA tile
-constexpr int kTileN = 128;   // output channels per CTA tile (TMEM columns)
-constexpr int kBlockK = 32;   // input channels per pipeline stage
-constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one A or B operand tile
-constexpr int kConvThreads = 256;  // warp 0: TMA + MMA issue; warps 4-7: transform + epilogue
+constexpr int kTileN = 128;   // accumulator columns (output channels per CTA tile, N extent <= 128)
+constexpr int kBlockK = 32;   // input channels per pipeline step
+constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one weight operand tile (hi or lo)
+constexpr int kConvThreads = 256;
+constexpr int kStagesA = 2;       // activation operand stages in TMEM
+constexpr int kTmemCols = 256;    // 128 accumulator columns + kStagesA x (A_hi 32 + A_lo 32)
+constexpr int kMaxStagesB = 4;
+constexpr int kMaxRaw = 2;
 
 struct ConvArgs {
   float* y;
   const float* bias;      // [Cout] or null
   const float* residual;  // same shape as y or null
+  const float* gate;      // same shape as y or null: result is zeroed where gate <= 0 (ReLU backward mask)
   int B, Cin, Cout, H, W;
   int taps;               // 9 (3x3, pad 1) or 1
   int relu_in;            // apply relu to the input on the fly
   int relu_out;           // apply relu to the output
-  int rows_per_tile;      // image rows per 128-pixel tile (box H extent)
+  int rows_per_tile;      // image rows per 128-pixel tile (box H extent without halo)
   int imgs_per_tile;      // images per tile (box B extent)
   int k_blocks;           // ceil(Cin / 32)
   int box_w, box_h;       // raw activation box extents (W + 8, rows + 2 with a halo for 3x3; W, rows for 1x1)
-  int raw_bytes;          // bytes of one raw box (all 32 channels, all images of the tile)
-  int debug;              // bring-up: 0 = full kernel; 1 stop after setup; 2 after first TMA; 3 after transform; 4 after first MMA
+  int raw_bytes;          // ring pitch of the raw boxes (box bytes rounded up to 1024)
+  int raw_tx;             // true bytes of one raw box (all 32 channels, all images of the tile)
+  int n_tile;             // MMA N extent: 112 when Cout <= 112 (13% less weight traffic and MMA time), else 128
+  int n_raw, n_b;         // ring depths: raw boxes, weight tiles
+  int debug;              // profiling aid (MFLOW_CONV_DEBUG): bit0 skip MMAs, bit1 skip transform math, bit2 skip stores
 };
 
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -55,124 +68,141 @@ __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__
 // split is pre-rounded to keep the truncation from biasing the sum
 __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_ahi = smem;
-  uint8_t* s_alo = smem + kStageBytes;
-  float* s_bhi = (float*)(smem + 2 * kStageBytes);
-  float* s_blo = (float*)(smem + 3 * kStageBytes);
-  float* s_raw = (float*)(smem + 4 * kStageBytes);
-  __shared__ __align__(8) uint64_t bar_raw, bar_full, bar_mma;
+  uint8_t* s_b = smem;                              // n_b x {B_hi 16 KB, B_lo 16 KB}
+  uint8_t* s_raw = s_b + a.n_b * 2 * kStageBytes;   // n_raw x raw box
+  __shared__ __align__(8) uint64_t raw_full[kMaxRaw], raw_empty[kMaxRaw], b_full[kMaxStagesB], b_empty[kMaxStagesB],
+      a_full[kStagesA], a_empty[kStagesA], acc_full;
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * kTileN;
-  // tile -> first (image, row)
   const int tiles_per_img = a.imgs_per_tile > 1 ? 1 : a.H / a.rows_per_tile;
   const int b0 = a.imgs_per_tile > 1 ? tile * a.imgs_per_tile : tile / tiles_per_img;
   const int h0 = a.imgs_per_tile > 1 ? 0 : (tile % tiles_per_img) * a.rows_per_tile;
+  const int pad = a.taps == 9 ? 1 : 0;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_whi);
     prefetch_tensormap(&map_wlo);
-    mbar_init(&bar_raw, 1);
-    mbar_init(&bar_full, 1);
-    mbar_init(&bar_mma, 1);
+    for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
+    for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&s_tmem, kTileN);
+  if (warp == 1) tmem_alloc(&s_tmem, kTmemCols);  // [0,128) accumulator, then kStagesA x {A_hi, A_lo} x 32 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  const uint32_t idesc = idesc_tf32(kTileM, kTileN, /*a K-major*/ 0, /*b K-major*/ 0);
-  // pixel owned by this transform / epilogue thread
-  const int pm = (threadIdx.x - 128) & 127;
-  const int pw = pm % a.W, pg = pm / a.W;
-  const int phl = pg % a.rows_per_tile, pbl = pg / a.rows_per_tile;
-  const int chan_stride = a.box_h * a.box_w;                            // floats between channels in the raw box
-  const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
-  const int pad = a.taps == 9 ? 1 : 0;
-  uint32_t phase = 0, raw_phase = 0;
-  uint32_t accumulate = 0;
-  for (int kb = 0; kb < a.k_blocks; ++kb) {
-    // one raw box per channel block: the tile's pixels plus a one-pixel halo (the innermost TMA
-    // coordinate must be a multiple of 16 bytes, so the box starts 4 pixels to the left); all 9 taps
-    // of the 3x3 stencil are cut out of it by the transform warps
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&bar_raw, a.raw_bytes);
-      tma_load_4d(s_raw, &map_x, &bar_raw, pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
-    }
-    const int valid = min(kBlockK, a.Cin - kb * kBlockK);
-    const int ksteps = (valid + 7) / 8;
-    for (int tap = 0; tap < a.taps; ++tap) {
-      const int dy = pad ? tap / 3 : 0, dx = pad ? tap % 3 : 0;
-      if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar_full, 2 * kStageBytes);
-        tma_load_3d(s_bhi, &map_whi, &bar_full, kb * kBlockK, n0, tap);
-        tma_load_3d(s_blo, &map_wlo, &bar_full, kb * kBlockK, n0, tap);
-      }
-      if (tap == 0) { mbar_wait(&bar_raw, raw_phase); raw_phase ^= 1; }
-      // transform: thread = pixel; gather its 32 channels of this tap, optional ReLU, TF32 hi / lo split,
-      // write the pixel's 128-byte row of both K-major operand tiles (16-byte chunk j -> slot j ^ (row & 7))
-      if (warp >= 4) {
-        uint8_t* row_hi = s_ahi + pm * 128;
-        uint8_t* row_lo = s_alo + pm * 128;
-        const float* src = s_raw + raw_base + (pad ? dy * a.box_w + dx + 3 : 0);
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          float4 h, l;
-          float v0 = src[(4 * jj + 0) * chan_stride], v1 = src[(4 * jj + 1) * chan_stride];
-          float v2 = src[(4 * jj + 2) * chan_stride], v3 = src[(4 * jj + 3) * chan_stride];
-          if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-          h.x = tf32_trunc(v0); h.y = tf32_trunc(v1); h.z = tf32_trunc(v2); h.w = tf32_trunc(v3);
-          l.x = tf32_round(v0 - h.x); l.y = tf32_round(v1 - h.y); l.z = tf32_round(v2 - h.z); l.w = tf32_round(v3 - h.w);
-          const int slot = (jj ^ (pm & 7)) * 16;
-          *reinterpret_cast<float4*>(row_hi + slot) = h;
-          *reinterpret_cast<float4*>(row_lo + slot) = l;
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        const int rb = kb % a.n_raw;
+        mbar_wait(&raw_empty[rb], ((kb / a.n_raw) & 1) ^ 1);
+        mbar_expect_tx(&raw_full[rb], a.raw_tx);
+        tma_load_4d(s_raw + rb * a.raw_bytes, &map_x, &raw_full[rb], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+        for (int tap = 0; tap < a.taps; ++tap, ++it) {
+          const int sb = it % a.n_b;
+          mbar_wait(&b_empty[sb], ((it / a.n_b) & 1) ^ 1);
+          mbar_expect_tx(&b_full[sb], 2 * a.n_tile * kBlockK * 4);
+          tma_load_3d(s_b + sb * 2 * kStageBytes, &map_whi, &b_full[sb], kb * kBlockK, n0, tap);
+          tma_load_3d(s_b + sb * 2 * kStageBytes + kStageBytes, &map_wlo, &b_full[sb], kb * kBlockK, n0, tap);
         }
-        fence_proxy_async();
       }
-      mbar_wait(&bar_full, phase);
-      __syncthreads();
-      if (threadIdx.x == 0) {
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(kTileM, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      uint32_t accumulate = 0;
+      int it = 0;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        const int valid = min(kBlockK, a.Cin - kb * kBlockK);
+        const int ksteps = (a.debug & 1) ? 0 : (valid + 7) / 8;
+        for (int tap = 0; tap < a.taps; ++tap, ++it) {
+          const int sa = it % kStagesA, sb = it % a.n_b;
+          mbar_wait(&a_full[sa], (it / kStagesA) & 1);
+          mbar_wait(&b_full[sb], (it / a.n_b) & 1);
+          tc_fence_after();
+          const uint32_t ahi = tmem + kTileN + sa * 2 * kBlockK, alo = ahi + kBlockK;
+          const uint32_t bhi = smem_u32(s_b + sb * 2 * kStageBytes), blo = bhi + kStageBytes;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes further along each row
+            const uint64_t d_bhi = smem_desc(bhi + kk * 32, 16, 1024, 2), d_blo = smem_desc(blo + kk * 32, 16, 1024, 2);
+            umma_tf32_ts(tmem, ahi + kk * 8, d_bhi, idesc, accumulate);
+            umma_tf32_ts(tmem, alo + kk * 8, d_bhi, idesc, 1);
+            umma_tf32_ts(tmem, ahi + kk * 8, d_blo, idesc, 1);
+            accumulate = 1;
+          }
+          umma_commit(&a_empty[sa]);  // slots are free again once these MMAs have read them
+          umma_commit(&b_empty[sb]);
+        }
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (warp >= 4) {
+    // ===== activation transform: thread = pixel = TMEM lane =====
+    const int pm = threadIdx.x - 128;
+    const int pw = pm % a.W, pg = pm / a.W;
+    const int phl = pg % a.rows_per_tile, pbl = pg / a.rows_per_tile;
+    const int chan_stride = a.box_h * a.box_w;                              // floats between channels in the raw box
+    const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
+    const uint32_t t_lane = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+    int it = 0;
+    for (int kb = 0; kb < a.k_blocks; ++kb) {
+      const int rb = kb % a.n_raw;
+      mbar_wait(&raw_full[rb], (kb / a.n_raw) & 1);
+      const float* raw = reinterpret_cast<const float*>(s_raw + rb * a.raw_bytes) + raw_base;
+      for (int tap = 0; tap < a.taps; ++tap, ++it) {
+        const int dy = pad ? tap / 3 : 0, dx = pad ? tap % 3 : 0;
+        const int sa = it % kStagesA;
+        mbar_wait(&a_empty[sa], ((it / kStagesA) & 1) ^ 1);
         tc_fence_after();
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t d_ahi = smem_desc(smem_u32(s_ahi) + kk * 32, 16, 1024, 2);
-          const uint64_t d_alo = smem_desc(smem_u32(s_alo) + kk * 32, 16, 1024, 2);
-          const uint64_t d_bhi = smem_desc(smem_u32(s_bhi) + kk * 32, 16, 1024, 2);
-          const uint64_t d_blo = smem_desc(smem_u32(s_blo) + kk * 32, 16, 1024, 2);
-          umma_tf32(tmem, d_ahi, d_bhi, idesc, accumulate);
-          umma_tf32(tmem, d_alo, d_bhi, idesc, 1);
-          umma_tf32(tmem, d_ahi, d_blo, idesc, 1);
-          accumulate = 1;
+        // gather the pixel's 32 channels of this tap, optional ReLU, TF32 hi / lo split, and store both
+        // parts into this thread's TMEM lane (32 columns each)
+        const float* src = raw + (pad ? dy * a.box_w + dx + 3 : 0);
+        if (!(a.debug & 2)) {
+          float hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float v = src[c * chan_stride];
+            if (a.relu_in) v = fmaxf(v, 0.f);
+            hi[c] = tf32_trunc(v);
+            lo[c] = tf32_round(v - hi[c]);
+          }
+          const uint32_t t_a = t_lane + kTileN + sa * 2 * kBlockK;
+          tmem_st_32x32(t_a, hi);
+          tmem_st_32x32(t_a + kBlockK, lo);
+          tmem_st_wait();
         }
-        umma_commit(&bar_mma);
+        tc_fence_before();
+        mbar_arrive(&a_full[sa]);
       }
-      mbar_wait(&bar_mma, phase);  // operands consumed: the tiles (and, after the last tap, the raw box) may be overwritten
-      phase ^= 1;
+      mbar_arrive(&raw_empty[rb]);
     }
-  }
-  // ---- epilogue: TMEM -> registers -> NCHW global, bias / residual / ReLU fused ----
-  tc_fence_after();
-  if (warp >= 4) {
-    const int ew = warp - 4;           // TMEM lane quarter this warp may access
-    const int w = pw;                  // pixel index inside the tile == TMEM lane == pm
+    // ===== epilogue: TMEM -> registers -> NCHW global, bias / residual / ReLU / mask fused =====
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
     const int b = b0 + pbl, h = h0 + phl;
-    const bool ok = b < a.B;
+    const bool ok = b < a.B && !(a.debug & 4);
     const int64_t plane = (int64_t)a.H * a.W;
-    const int64_t base = ((int64_t)b * a.Cout) * plane + (int64_t)h * a.W + w;
+    const int64_t base = ((int64_t)b * a.Cout) * plane + (int64_t)h * a.W + pw;
 #pragma unroll 1
     for (int c0 = 0; c0 < kTileN; c0 += 32) {
       if (n0 + c0 >= a.Cout) break;
       float v[32];
-      tmem_ld_32x32(tmem + ((uint32_t)(ew * 32) << 16) + c0, v);
+      tmem_ld_32x32(t_lane + c0, v);
       if (ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -181,6 +211,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             float r = v[j] + (a.bias ? a.bias[co] : 0.f);
             if (a.residual) r += a.residual[base + co * plane];
             if (a.relu_out) r = fmaxf(r, 0.f);
+            if (a.gate) r = a.gate[base + co * plane] > 0.f ? r : 0.f;
             a.y[base + co * plane] = r;
           }
         }
@@ -189,7 +220,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, kTileN);
+  if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -225,7 +256,8 @@ static bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* 
 using namespace mflow;
 
 extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const float* x, const float* w_hi, const float* w_lo,
-                                             const float* bias, const float* residual, float* y, void* stream) {
+                                             const float* bias, const float* residual, const float* gate, float* y,
+                                             void* stream) {
   MFLOW_REQUIRE(d && x && w_hi && w_lo && y, "null pointer");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
   MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
@@ -236,18 +268,28 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   if (d->batch == 0) return MFLOW_OK;
   const int W = (int)d->width, H = (int)d->height, B = (int)d->batch;
   ConvArgs a{};
-  a.y = y; a.bias = bias; a.residual = residual;
+  a.y = y; a.bias = bias; a.residual = residual; a.gate = gate;
   a.B = B; a.Cin = (int)d->c_in; a.Cout = (int)d->c_out; a.H = H; a.W = W;
   a.taps = d->kernel == 3 ? 9 : 1;
   a.relu_in = d->relu_in; a.relu_out = d->relu_out;
-  const int groups = kTileM / W;                       // (image,row) groups per tile
+  const int groups = kTileM / W;  // (image, row) groups per tile
   a.rows_per_tile = groups < H ? groups : H;
   a.imgs_per_tile = groups / a.rows_per_tile;
   a.k_blocks = (a.Cin + kBlockK - 1) / kBlockK;
   a.box_w = a.taps == 9 ? W + 8 : W;
   a.box_h = a.taps == 9 ? a.rows_per_tile + 2 : a.rows_per_tile;
-  a.raw_bytes = a.box_w * a.box_h * kBlockK * a.imgs_per_tile * 4;
-  a.debug = 0;
+  a.raw_tx = a.box_w * a.box_h * kBlockK * a.imgs_per_tile * 4;
+  a.raw_bytes = (a.raw_tx + 1023) / 1024 * 1024;
+  a.n_tile = a.Cout <= 112 ? 112 : 128;
+  { const char* dbg = getenv("MFLOW_CONV_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+  // Ring depths: prefer a footprint that lets two CTAs share an SM (each at most ~110 KB), which hides one
+  // CTA's prologue / epilogue behind the other's main loop; fall back to deeper rings, one CTA per SM.
+  const int two_cta_budget = 110 * 1024, one_cta_budget = 225 * 1024;
+  const int steps = a.k_blocks * a.taps;
+  a.n_b = steps < 2 ? 1 : 2; a.n_raw = 1;
+  if (a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes > two_cta_budget) { a.n_b = 4; a.n_raw = 1; }
+  MFLOW_REQUIRE(a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes <= one_cta_budget, "tile does not fit in shared memory");
+
   CUtensorMap mx, mhi, mlo;
   {  // activations, NCHW: dims (W, H, C, B); box lands in shared memory as [image][channel][row][w]
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
@@ -255,16 +297,16 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.box_h, (cuuint32_t)kBlockK, (cuuint32_t)a.imgs_per_tile};
     if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
-  {  // weights: [taps][n_pad][k_pad], K-major 128B-swizzled tiles of 128 x 32
+  {  // weights: [taps][n_pad][k_pad], K-major 128B-swizzled tiles of n_tile x 32
     cuuint64_t dims[3] = {(cuuint64_t)d->k_pad, (cuuint64_t)d->n_pad, (cuuint64_t)a.taps};
     cuuint64_t str[2] = {(cuuint64_t)d->k_pad * 4, (cuuint64_t)d->k_pad * d->n_pad * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)a.n_tile, 1};
     if (!encode(&mhi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
     if (!encode(&mlo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
   }
   const int n_tiles = a.imgs_per_tile > 1 ? (B + a.imgs_per_tile - 1) / a.imgs_per_tile : B * (H / a.rows_per_tile);
   dim3 grid(n_tiles, (a.Cout + kTileN - 1) / kTileN);
-  const size_t smem = 4 * kStageBytes + a.raw_bytes + 1024;
+  const size_t smem = (size_t)a.n_b * 2 * kStageBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

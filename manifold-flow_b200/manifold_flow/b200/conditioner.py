@@ -1,15 +1,18 @@
 """Dense contractions of the conditioner networks (kernel (b) of the north star).
 
-Round-1 state: the GEMMs / convolutions are issued as plain library calls (cuBLAS / cuDNN through
-ATen) in full fp32 - TF32 is switched off around them unless ``config.conditioner_math == "tf32"`` -
-so that the spline kernels see bit-faithful parameters.  The hand-written tcgen05 + TMA
-implicit-GEMM kernels replace these calls behind the same four functions.
+Image conditioners (``ConvResidualNet``): every 3x3 / 1x1 convolution - forward and data gradient - runs
+on the tcgen05 tensor cores through ``mflow_conv2d_tf32x3`` (TMA-fed implicit GEMM on NCHW tensors,
+3xTF32 split for fp32 accuracy, pre-activation ReLU, bias, residual add and the ReLU mask of the backward
+pass fused).  Still library calls in this round: the weight gradients of those convolutions (cuDNN), the
+small vector conditioners (``ResidualNet``: cuBLAS GEMMs with M = batch) and the GLU context path; TF32 is
+switched off around them unless ``config.conditioner_math == "tf32"``.
 """
 import contextlib
 
 import torch
 from torch.nn import functional as F
 
+from . import ops
 from .cabi import require_cuda
 from .config import config
 
@@ -32,9 +35,15 @@ def linear(x, layer):
         return F.linear(x, layer.weight, layer.bias)
 
 
+def _use_tc(x, layer):
+    return config.conv_tensor_cores and config.conditioner_math == "fp32" and ops.conv_tc_supported(x, layer.weight)
+
+
 def conv(x, layer):
     require_cuda(x)
     with _math_mode():
+        if _use_tc(x, layer):
+            return ops.conv_tc(x, layer.weight, layer.bias)
         return F.conv2d(x, layer.weight, layer.bias, padding=layer.padding)
 
 
@@ -53,6 +62,9 @@ def residual_block_conv(x, conv0, conv1, gate_layer, context):
     """nn/resnet.py:91-104"""
     require_cuda(x)
     with _math_mode():
+        if gate_layer is None and _use_tc(x, conv0):
+            t = ops.conv_tc(x, conv0.weight, conv0.bias, relu_in=True)
+            return ops.conv_tc(t, conv1.weight, conv1.bias, residual=x, relu_in=True)
         t = F.conv2d(F.relu(x), conv0.weight, conv0.bias, padding=1)
         t = F.conv2d(F.relu(t), conv1.weight, conv1.bias, padding=1)
         if gate_layer is not None:

@@ -6,6 +6,8 @@ class _Config:
     # "fp32": conditioner GEMMs/convolutions reproduce the reference's fp32 results (parity mode)
     # "tf32": single-pass TF32 tensor-core math (throughput sweeps; not parity-clean)
     conditioner_math = os.environ.get("MFLOW_CONDITIONER_MATH", "fp32")
+    # image-conditioner convolutions on the tcgen05 tensor cores (3xTF32); False = cuDNN fp32 library calls
+    conv_tensor_cores = os.environ.get("MFLOW_CONV_TC", "1") != "0"
     # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch
     fuse_linear_glue = os.environ.get("MFLOW_FUSE_GLUE", "1") != "0"
     # full_jacobian=True: the reference's Permutation Jacobian is the transpose of the exact one

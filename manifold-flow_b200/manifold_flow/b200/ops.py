@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import cabi
-from .cabi import MixDesc, RqsDesc, check, lib, ptr, require_cuda, stream
+from .cabi import ConvDesc, MixDesc, RqsDesc, check, lib, ptr, require_cuda, stream
 
 
 def _c(t):
@@ -189,6 +189,103 @@ def rqs_search(knots, values):
     check(lib().mflow_rqs_search(ptr(knots), ptr(values), ptr(bins), values.numel(), knots.shape[-1] - 1, stream()), "mflow_rqs_search")
     cabi.count_launch()
     return bins
+
+
+# --------------------------------------------------------------------------------------------
+# (b) conditioner convolutions on tcgen05 tensor cores (3xTF32)
+# --------------------------------------------------------------------------------------------
+TC_WIDTHS = (4, 8, 16, 32)
+
+
+def conv_tc_supported(x, weight):
+    return (x.dim() == 4 and x.shape[2] == x.shape[3] and x.shape[3] in TC_WIDTHS and weight.shape[2] == weight.shape[3]
+            and weight.shape[2] in (1, 3))
+
+
+def _split_weight(w_taps):
+    """[taps, N, K] fp32 -> (hi, lo), zero padded to N % 128 == 0 and K % 32 == 0: hi = TF32 truncation
+    of w, lo = (w - hi) rounded to TF32, so that hi + lo reproduces w to ~2^-22."""
+    taps, n, k = w_taps.shape
+    n_pad, k_pad = (n + 127) // 128 * 128, (k + 31) // 32 * 32
+    wt = torch.zeros(taps, n_pad, k_pad, dtype=torch.float32, device=w_taps.device)
+    wt[:, :n, :k] = w_taps
+    hi = (wt.view(torch.int32) & -8192).view(torch.float32)
+    lo = (((wt - hi).view(torch.int32) + 4096) & -8192).view(torch.float32)
+    return hi.contiguous(), lo.contiguous(), n_pad, k_pad
+
+
+class _WeightCache:
+    """Split / padded operand copies of a convolution weight, rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self._entries = {}
+
+    def get(self, weight, transposed):
+        key = (id(weight), transposed)
+        ver = (weight.data_ptr(), weight._version)
+        ent = self._entries.get(key)
+        if ent is None or ent[0] != ver:
+            with torch.no_grad():
+                co, ci, kh, kw = weight.shape
+                if not transposed:  # forward: W[tap][co][ci]
+                    taps = weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+                else:  # data gradient: correlation with the taps flipped and channels swapped
+                    taps = weight.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+                ent = (ver, _split_weight(taps))
+            self._entries[key] = ent
+        return ent[1]
+
+
+_weight_cache = _WeightCache()
+
+
+def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in):
+    hi, lo, n_pad, k_pad = split
+    b, c_in, h, w = x.shape
+    d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0,
+                 n_pad=n_pad, k_pad=k_pad)
+    y = torch.empty((b, c_out, h, w), dtype=torch.float32, device=x.device)
+    check(lib().mflow_conv2d_tf32x3(ctypes.byref(d), ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(residual), ptr(gate), ptr(y), stream()),
+          "mflow_conv2d_tf32x3")
+    cabi.count_launch()
+    return y
+
+
+class _ConvTC(torch.autograd.Function):
+    """y = conv2d(relu?(x), W) + b (+ residual), 3x3 pad 1 or 1x1, NCHW fp32, on the tensor cores.
+    Backward: data gradient through the same kernel (transposed / flipped weights, ReLU mask fused in the
+    epilogue); weight gradient as a library call (cuDNN) for now; bias gradient a reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu_in):
+        require_cuda(x, weight, bias, residual)
+        x = _c(x)
+        residual = None if residual is None else _c(residual)
+        kernel = weight.shape[2]
+        y = _conv_tc_launch(x, _weight_cache.get(weight, False), weight.shape[0], kernel, bias, residual, None, relu_in)
+        ctx.save_for_backward(x, weight)
+        ctx.relu_in, ctx.has_bias, ctx.has_res = relu_in, bias is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = _c(g)
+        gx = gw = gb = None
+        kernel = weight.shape[2]
+        if ctx.needs_input_grad[0]:
+            gx = _conv_tc_launch(g, _weight_cache.get(weight, True), weight.shape[1], kernel, None, None, x if ctx.relu_in else None, False)
+        if ctx.needs_input_grad[1]:
+            xin = torch.relu(x) if ctx.relu_in else x
+            gw = torch.ops.aten.convolution_backward(g, xin, weight, None, [1, 1], [kernel // 2] * 2, [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(dim=(0, 2, 3))
+        return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None
+
+
+def conv_tc(x, weight, bias=None, residual=None, relu_in=False):
+    return _ConvTC.apply(x, weight, bias, residual, bool(relu_in))
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,84 @@
+"""GPU parity of kernel (b): tcgen05 / TMA 3xTF32 convolutions against fp64 and against cuDNN fp32,
+forward and backward, for every feature-map size and both kernel sizes of ConvResidualNet."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # (batch, c_in, c_out, hw, kernel)
+    (2, 100, 100, 32, 3), (3, 100, 100, 16, 3), (5, 100, 100, 8, 3), (9, 100, 100, 4, 3), (1, 100, 100, 4, 3),
+    (2, 6, 100, 32, 1), (2, 12, 100, 16, 1), (3, 24, 100, 8, 1), (2, 48, 100, 4, 1),
+    (2, 100, 192, 32, 1), (2, 100, 384, 16, 1), (2, 100, 768, 8, 1), (3, 100, 1536, 4, 1), (2, 16, 16, 8, 3),
+]
+
+
+def _rel(a, b):
+    return float((a.double() - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("relu_in", [False, True])
+def test_conv_forward_backward_vs_fp64(cuda_device, case, relu_in):
+    from manifold_flow.b200 import ops
+
+    b, ci, co, hw, k = case
+    g = torch.Generator().manual_seed(b * 1000 + ci + co + hw)
+    x = torch.randn(b, ci, hw, hw, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) * (1.0 / (ci * k * k) ** 0.5)
+    bias = torch.randn(co, generator=g)
+    res = torch.randn(b, co, hw, hw, generator=g)
+    gy = torch.randn(b, co, hw, hw, generator=g)
+
+    def run(dtype, device, fn):
+        leaves = [t.detach().clone().to(device=device, dtype=dtype).requires_grad_(True) for t in (x, w, bias, res)]
+        y = fn(*leaves)
+        y.backward(gy.to(device=device, dtype=dtype))
+        return [y.detach()] + [t.grad for t in leaves]
+
+    ref_fn = lambda xx, ww, bb, rr: F.conv2d(F.relu(xx) if relu_in else xx, ww, bb, padding=k // 2) + rr
+    ref = run(torch.float64, "cpu", ref_fn)
+    torch.backends.cudnn.allow_tf32 = False
+    lib32 = run(torch.float32, cuda_device, ref_fn)
+    got = run(torch.float32, cuda_device, lambda xx, ww, bb, rr: ops.conv_tc(xx, ww, bb, residual=rr, relu_in=relu_in))
+    names = ["y", "grad_x", "grad_w", "grad_b", "grad_res"]
+    for name, a, l, r in zip(names, got, lib32, ref):
+        e_got, e_lib = _rel(a.cpu(), r), _rel(l.cpu(), r)
+        # fp32-accurate: within 1e-5 of the fp64 result and no worse than 8x the fp32 library path
+        assert e_got <= max(2e-5, 8 * e_lib), f"{name}: rel L2 error {e_got:.2e} (cuDNN fp32: {e_lib:.2e})"
+
+
+def test_conv_resnet_matches_library_path(cuda_device):
+    """ConvResidualNet through the tensor-core path == through cuDNN fp32, forward and gradients."""
+    from manifold_flow import nn as nn_
+    from manifold_flow.b200 import config
+
+    torch.manual_seed(3)
+    net = nn_.ConvResidualNet(6, 6 * 32, hidden_channels=100, num_blocks=2).to(cuda_device)
+    x = torch.randn(4, 6, 32, 32, device=cuda_device)
+    gy = torch.randn(4, 192, 32, 32, device=cuda_device)
+
+    def run(flag):
+        config.conv_tensor_cores = flag
+        try:
+            net.zero_grad()
+            xx = x.clone().requires_grad_(True)
+            y = net(xx)
+            y.backward(gy)
+            return [y.detach(), xx.grad] + [p.grad.clone() for p in net.parameters()]
+        finally:
+            config.conv_tensor_cores = True
+
+    a, b = run(True), run(False)
+    for u, v in zip(a, b):
+        assert _rel(u, v.double()) <= 2e-3  # two fp32 paths; cuDNN picks non-deterministic wgrad algorithms
+
+
+def test_unsupported_shapes_fall_back_loudly(cuda_device):
+    from manifold_flow.b200 import ops
+
+    x = torch.randn(2, 8, 12, 12, device=cuda_device)
+    w = torch.randn(8, 8, 3, 3, device=cuda_device)
+    assert not ops.conv_tc_supported(x, w)
+    with pytest.raises(ValueError):
+        ops.conv_tc(x, w)
