@@ -6,6 +6,7 @@ or an unsupported shape raises.
 """
 import ctypes
 import math
+import weakref
 
 import torch
 
@@ -215,25 +216,29 @@ def _split_weight(w_taps):
 
 
 class _WeightCache:
-    """Split / padded operand copies of a convolution weight, rebuilt when the parameter changes."""
+    """Split / padded operand copies of a convolution weight, rebuilt when the parameter changes.
+    Entries are bound to the tensor object itself (weak reference), not just to its id(): Python reuses
+    ids, and a new tensor can land on the same address with the same version counter."""
 
     def __init__(self):
         self._entries = {}
 
     def get(self, weight, transposed):
         key = (id(weight), transposed)
-        ver = (weight.data_ptr(), weight._version)
+        ver = (weight.data_ptr(), weight._version, tuple(weight.shape))
         ent = self._entries.get(key)
-        if ent is None or ent[0] != ver:
+        if ent is None or ent[0]() is not weight or ent[1] != ver:
+            if len(self._entries) > 4096:
+                self._entries = {k: v for k, v in self._entries.items() if v[0]() is not None}
             with torch.no_grad():
                 co, ci, kh, kw = weight.shape
                 if not transposed:  # forward: W[tap][co][ci]
                     taps = weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
                 else:  # data gradient: correlation with the taps flipped and channels swapped
                     taps = weight.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
-                ent = (ver, _split_weight(taps))
+                ent = (weakref.ref(weight), ver, _split_weight(taps))
             self._entries[key] = ent
-        return ent[1]
+        return ent[2]
 
 
 _weight_cache = _WeightCache()
