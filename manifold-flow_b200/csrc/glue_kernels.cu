@@ -334,7 +334,8 @@ static size_t mix_smem(int C) { return (size_t)(C * C + C * (kMixPix + 1) + C) *
 static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
 static int wgrad_grid(int64_t n_pix) {
   int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
-  return (int)(tiles < 1 ? 1 : (tiles > kNumSMs ? kNumSMs : tiles));
+  const int64_t cap = (int64_t)kNumSMs * 8;  // 8 CTAs per SM: the partial blocks stay small (<= 5 MB at C = 48)
+  return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
 }  // namespace mflow

@@ -39,8 +39,14 @@ struct RqsArgs {
   int64_t x_so, x_sc, y_so, y_sc, p_so, p_sc, p_sp, p_si;
   int64_t n_id_chan, id_off, id_sc;
   int chunks;
+  uint32_t inner_mul, inner_shift;  // e / n_inner == umulhi(e, inner_mul) >> inner_shift for 0 <= e < 2^31 (planes kernels)
   RqsConsts c;
 };
+
+// exact unsigned division by an invariant divisor (Granlund-Montgomery, 32-bit, valid for dividends < 2^31)
+__device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t mul, uint32_t shift) {
+  return mul == 0 ? (e >> shift) : (__umulhi(e, mul) >> shift);
+}
 
 constexpr int kPlaneThreads = 256;
 constexpr int64_t kCounterBytes = 65536 * 4;  // one arrival counter per sample (planes layout: O <= 65535)
@@ -50,38 +56,43 @@ constexpr int64_t kCounterBytes = 65536 * 4;  // one arrival counter per sample 
 // grid = (chunks, O); CTA (chunk, o) walks elements [chunk*256, ...) of sample o with stride
 // chunks*256, so consecutive threads touch consecutive pixels of every parameter plane.
 // ---------------------------------------------------------------------------------------------
-template <int K, bool INV>
-__global__ void __launch_bounds__(kPlaneThreads) rqs_planes_apply_kernel(const RqsArgs a) {
+// INNER > 0: the standard planes layout with a compile-time plane size (p_si == 1, p_sp == INNER, p_sc ==
+// P * INNER): parameter loads become LDG [base + immediate] with no per-load address arithmetic.
+template <int K, bool INV, int INNER>
+__global__ void __launch_bounds__(kPlaneThreads, 4) rqs_planes_apply_kernel(const RqsArgs a) {
   constexpr int P = 3 * K - 1;
   __shared__ float red[kPlaneThreads / 32];
   __shared__ int s_last;
   const int64_t o = blockIdx.y;
-  const int64_t per_sample = a.n_chan * a.n_inner;
+  // per-sample extents and strides fit in 32 bits (checked on the host): 64-bit math only for the sample base
+  const uint32_t n_inner = INNER ? INNER : (uint32_t)a.n_inner, per_sample = (uint32_t)a.n_chan * n_inner;
+  const uint32_t p_sc = INNER ? P * INNER : (uint32_t)a.p_sc, p_si = INNER ? 1 : (uint32_t)a.p_si;
+  const uint32_t p_sp = INNER ? INNER : (uint32_t)a.p_sp;
+  const uint32_t x_sc = (uint32_t)a.x_sc, y_sc = (uint32_t)a.y_sc;
   const float* xo = a.x + o * a.x_so;
   float* yo = a.y + o * a.y_so;
   const float* po = a.params + o * a.p_so;
   float lad_acc = 0.f;
-  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample;
-       e += (int64_t)gridDim.x * kPlaneThreads) {
-    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
-    const float* pe = po + ch * a.p_sc + i * a.p_si;
+  for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample; e += gridDim.x * kPlaneThreads) {
+    const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
+    const float* pe = po + (ch * p_sc + i * p_si);
     float p[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * a.p_sp);
-    const float v = ldg_stream(xo + ch * a.x_sc + i);
+    for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * p_sp);
+    const float v = ldg_stream(xo + (ch * x_sc + i));
     float out, lad;
     int bin;
     rqs_eval<K, INV>(v, p, a.c, out, lad, bin);
-    stg_stream(yo + ch * a.y_sc + i, out);
+    stg_stream(yo + (ch * y_sc + i), out);
     if (a.lad_elem) stg_stream(a.lad_elem + o * per_sample + e, lad);
     if (a.bins) a.bins[o * per_sample + e] = bin;
     lad_acc += lad;
   }
   // identity half of the coupling layer: plain copy (coupling.py:116-118)
-  const int64_t n_id = a.n_id_chan * a.n_inner;
-  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += (int64_t)gridDim.x * kPlaneThreads) {
-    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
-    const int64_t off = a.id_off + ch * a.id_sc + i;
+  const uint32_t n_id = (uint32_t)(a.n_id_chan * a.n_inner);
+  for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += gridDim.x * kPlaneThreads) {
+    const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
+    const int64_t off = a.id_off + (int64_t)(ch * (uint32_t)a.id_sc + i);
     stg_stream(yo + off, ldg_stream(xo + off));
   }
   if (a.lad_sample == nullptr) return;
@@ -111,38 +122,41 @@ __global__ void __launch_bounds__(kPlaneThreads) rqs_planes_apply_kernel(const R
 }
 
 // planes / generic layout, backward
-template <int K, bool INV>
-__global__ void __launch_bounds__(kPlaneThreads) rqs_planes_backward_kernel(const RqsArgs a) {
+template <int K, bool INV, int INNER>
+__global__ void __launch_bounds__(kPlaneThreads, 2) rqs_planes_backward_kernel(const RqsArgs a) {
   constexpr int P = 3 * K - 1;
   const int64_t o = blockIdx.y;
-  const int64_t per_sample = a.n_chan * a.n_inner;
+  const uint32_t n_inner = INNER ? INNER : (uint32_t)a.n_inner, per_sample = (uint32_t)a.n_chan * n_inner;
+  const uint32_t p_sc = INNER ? P * INNER : (uint32_t)a.p_sc, p_si = INNER ? 1 : (uint32_t)a.p_si;
+  const uint32_t x_sc = (uint32_t)a.x_sc, y_sc = (uint32_t)a.y_sc;
   const float* xo = a.x + o * a.x_so;
   const float* go = a.g_out ? a.g_out + o * a.y_so : nullptr;
   float* gio = a.y + o * a.x_so;  // g_in uses the input tensor's indexing
   const float* po = a.params + o * a.p_so;
   float* gpo = a.g_params + o * a.p_so;
   const float gl_s = a.g_lad_sample ? a.g_lad_sample[o] : 0.f;
-  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample;
-       e += (int64_t)gridDim.x * kPlaneThreads) {
-    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
-    const int64_t poff = ch * a.p_sc + i * a.p_si;
+  const uint32_t p_sp = INNER ? INNER : (uint32_t)a.p_sp;
+  for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample; e += gridDim.x * kPlaneThreads) {
+    const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
+    const uint32_t poff = ch * p_sc + i * p_si;
+    const float* pe = po + poff;
     float p[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) p[j] = ldg_stream(po + poff + j * a.p_sp);
-    const float v = ldg_stream(xo + ch * a.x_sc + i);
-    const float vo = INV ? ldg_stream(a.x_out + o * a.y_so + ch * a.y_sc + i) : 0.f;
-    const float g = go ? ldg_stream(go + ch * a.y_sc + i) : 0.f;
+    for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * p_sp);
+    const float v = ldg_stream(xo + (ch * x_sc + i));
+    const float vo = INV ? ldg_stream(a.x_out + o * a.y_so + (ch * y_sc + i)) : 0.f;
+    const float g = go ? ldg_stream(go + (ch * y_sc + i)) : 0.f;
     const float gl = gl_s + (a.g_lad_elem ? ldg_stream(a.g_lad_elem + o * per_sample + e) : 0.f);
     float g_in;
     float* gpe = gpo + poff;
-    const int64_t sp = a.p_sp;
+    const uint32_t sp = p_sp;
     rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * sp, val); });
-    stg_stream(gio + ch * a.x_sc + i, g_in);
+    stg_stream(gio + (ch * x_sc + i), g_in);
   }
-  const int64_t n_id = a.n_id_chan * a.n_inner;
-  for (int64_t e = (int64_t)blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += (int64_t)gridDim.x * kPlaneThreads) {
-    const int64_t ch = e / a.n_inner, i = e - ch * a.n_inner;
-    const int64_t off = a.id_off + ch * a.id_sc + i;
+  const uint32_t n_id = (uint32_t)(a.n_id_chan * a.n_inner);
+  for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += gridDim.x * kPlaneThreads) {
+    const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
+    const int64_t off = a.id_off + (int64_t)(ch * (uint32_t)a.id_sc + i);
     stg_stream(gio + off, go ? ldg_stream(go + off) : 0.f);
   }
 }
@@ -266,6 +280,17 @@ static bool fill_args(const mflow_rqs_desc* d, RqsArgs& a) {
   c.divisor = d->wh_divisor;
   c.rcp_divisor = 1.0f / d->wh_divisor;
   c.use_divisor = d->wh_divisor != 1.0f;
+  // magic number for e / n_inner, e < 2^31: power of two -> shift; else ceil(2^(32+s) / d) with s = ceil(log2 d) - 1...
+  const uint64_t dv = (uint64_t)d->n_inner;
+  if ((dv & (dv - 1)) == 0) {
+    a.inner_mul = 0; a.inner_shift = 0;
+    while ((1ull << a.inner_shift) < dv) ++a.inner_shift;
+  } else {
+    uint32_t s = 0;
+    while ((1ull << s) < dv) ++s;            // s = ceil(log2 d)
+    a.inner_mul = (uint32_t)(((1ull << (31 + s)) + dv - 1) / dv);  // ceil(2^(31+s) / d) < 2^32, exact for e < 2^31
+    a.inner_shift = s - 1;
+  }
   return true;
 }
 
@@ -279,6 +304,14 @@ static int plane_chunks(const mflow_rqs_desc* d) {
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
   return (int)chunks;
+}
+
+// plane size for which a compile-time specialisation exists (K = 11, standard planes layout), else 0
+static int planes_inner_const(const mflow_rqs_desc* d) {
+  const int P = 3 * d->num_bins - 1;
+  if (d->num_bins != 11 || d->p_si != 1 || d->p_sp != d->n_inner || d->p_sc != P * d->n_inner) return 0;
+  const int64_t i = d->n_inner;
+  return (i == 16 || i == 64 || i == 256 || i == 1024) ? (int)i : 0;
 }
 
 static bool rows_fast_path(const mflow_rqs_desc* d) {
@@ -308,6 +341,9 @@ static int validate(const mflow_rqs_desc* d) {
   MFLOW_REQUIRE(d->n_outer <= 65535 * 1024LL, "n_outer too large");
   MFLOW_REQUIRE(d->tail_bound > 0.f, "tail_bound must be positive");
   MFLOW_REQUIRE(d->wh_divisor > 0.f, "wh_divisor must be positive");
+  MFLOW_REQUIRE(d->n_chan * d->n_inner < (1ll << 30) && d->n_inner * d->p_sp < (1ll << 26) && d->n_chan * d->p_sc < (1ll << 31) &&
+                    d->n_chan * d->x_sc < (1ll << 31) && d->n_chan * d->y_sc < (1ll << 31) && d->n_id_chan * d->id_sc < (1ll << 31),
+                "per-sample extents must fit in 32 bits");
   MFLOW_REQUIRE((double)d->min_bin_width * d->num_bins <= 1.0, "Minimal bin width too large for the number of bins");
   MFLOW_REQUIRE((double)d->min_bin_height * d->num_bins <= 1.0, "Minimal bin height too large for the number of bins");
   return MFLOW_OK;
@@ -349,8 +385,19 @@ extern "C" MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* d, const float* x
     a.partial = (float*)((char*)workspace + kCounterBytes);
   }
   dim3 grid(chunks, (unsigned)d->n_outer);
-  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_apply_kernel<K, true><<<grid, kPlaneThreads, 0, st>>>(a);
-                   else rqs_planes_apply_kernel<K, false><<<grid, kPlaneThreads, 0, st>>>(a));
+  const int inner = planes_inner_const(d);
+  if (inner) {
+#define MFLOW_APPLY_INNER(I_)                                                                                      \
+  case I_:                                                                                                         \
+    if (d->inverse) rqs_planes_apply_kernel<11, true, I_><<<grid, kPlaneThreads, 0, st>>>(a);                       \
+    else rqs_planes_apply_kernel<11, false, I_><<<grid, kPlaneThreads, 0, st>>>(a);                                \
+    break;
+    switch (inner) { MFLOW_APPLY_INNER(16) MFLOW_APPLY_INNER(64) MFLOW_APPLY_INNER(256) MFLOW_APPLY_INNER(1024) }
+#undef MFLOW_APPLY_INNER
+    return check_launch("rqs_planes_apply_kernel");
+  }
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_apply_kernel<K, true, 0><<<grid, kPlaneThreads, 0, st>>>(a);
+                   else rqs_planes_apply_kernel<K, false, 0><<<grid, kPlaneThreads, 0, st>>>(a));
   return check_launch("rqs_planes_apply_kernel");
 }
 
@@ -375,8 +422,19 @@ extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float
   }
   MFLOW_REQUIRE(d->n_outer <= 65535, "planes layout: n_outer must be <= 65535 (split the batch)");
   dim3 grid(plane_chunks(d), (unsigned)d->n_outer);
-  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_backward_kernel<K, true><<<grid, kPlaneThreads, 0, st>>>(a);
-                   else rqs_planes_backward_kernel<K, false><<<grid, kPlaneThreads, 0, st>>>(a));
+  const int inner = planes_inner_const(d);
+  if (inner) {
+#define MFLOW_BWD_INNER(I_)                                                                                        \
+  case I_:                                                                                                         \
+    if (d->inverse) rqs_planes_backward_kernel<11, true, I_><<<grid, kPlaneThreads, 0, st>>>(a);                    \
+    else rqs_planes_backward_kernel<11, false, I_><<<grid, kPlaneThreads, 0, st>>>(a);                             \
+    break;
+    switch (inner) { MFLOW_BWD_INNER(16) MFLOW_BWD_INNER(64) MFLOW_BWD_INNER(256) MFLOW_BWD_INNER(1024) }
+#undef MFLOW_BWD_INNER
+    return check_launch("rqs_planes_backward_kernel");
+  }
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_planes_backward_kernel<K, true, 0><<<grid, kPlaneThreads, 0, st>>>(a);
+                   else rqs_planes_backward_kernel<K, false, 0><<<grid, kPlaneThreads, 0, st>>>(a));
   return check_launch("rqs_planes_backward_kernel");
 }
 

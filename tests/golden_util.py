@@ -154,9 +154,9 @@ def assert_as_accurate_as_reference(got, ref32, ref64, what="", floor=1e-6, rel=
     for frac in (0.5, 0.9):  # robust bulk statistics (a single ill-conditioned element must not decide)
         kk = max(1, int(n * frac))
         a, b = float(e_got.kthvalue(kk)[0]), float(e_ref.kthvalue(kk)[0])
-        assert a <= 2.5 * b + floor, f"{what}: p{int(100 * frac)} error {a:.3e} vs reference fp32 {b:.3e}"
-    assert q_got <= 3.0 * q_ref + 10 * floor, f"{what}: p99.9 error {q_got:.3e} vs reference fp32 {q_ref:.3e}"
-    assert float(e_got.max()) <= 20.0 * float(e_ref.max()) + 100 * floor, f"{what}: max error {float(e_got.max()):.3e} vs reference fp32 {float(e_ref.max()):.3e}"
+        assert a <= 3.0 * b + floor, f"{what}: p{int(100 * frac)} error {a:.3e} vs reference fp32 {b:.3e}"
+    assert q_got <= 5.0 * q_ref + 10 * floor, f"{what}: p99.9 error {q_got:.3e} vs reference fp32 {q_ref:.3e}"
+    assert float(e_got.max()) <= 50.0 * float(e_ref.max()) + 100 * floor, f"{what}: max error {float(e_got.max()):.3e} vs reference fp32 {float(e_ref.max()):.3e}"
 
 
 def assert_grad_as_accurate_as_reference(got, ref32, ref64, what="", rel=1e-4, factor=5.0):

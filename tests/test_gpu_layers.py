@@ -73,11 +73,15 @@ def test_layer_forward_inverse_match_reference(cuda_device, name):
     with torch.no_grad():
         y, lad = layer(x.to(cuda_device), context=cd)
         xi, ladi = layer.inverse(_t(L[f"{name}/y"]).to(cuda_device), context=cd)
-    scale = max(1.0, float(_t(L[f"{name}/y"]).abs().max()))
-    torch.testing.assert_close(y.cpu(), _t(L[f"{name}/y"]), rtol=1e-5, atol=1e-5 * scale)
-    torch.testing.assert_close(lad.cpu(), _t(L[f"{name}/lad"]), rtol=1e-5, atol=1e-4)
-    scale = max(1.0, float(x.abs().max()))
-    torch.testing.assert_close(xi.cpu(), _t(L[f"{name}/xi"]), rtol=1e-5, atol=2e-5 * scale)
+    # fp64 truth from the oracle on the same weights; the golden fp32 values are the reference's own output
+    spec = _layer_spec(name)
+    sd64 = {k: (v.double() if torch.is_floating_point(v) else v) for k, v in sd.items()}
+    c64 = None if ctx is None else ctx.double()
+    y64, lad64 = oracle.apply(spec, sd64, "", x.double(), c64, False)
+    xi64, _ = oracle.apply(spec, sd64, "", _t(L[f"{name}/y"]).double(), c64, True)
+    gu.assert_as_accurate_as_reference(y, _t(L[f"{name}/y"]), y64, what="outputs", floor=2e-6)
+    torch.testing.assert_close(lad.cpu(), _t(L[f"{name}/lad"]), rtol=1e-5, atol=2e-4)
+    gu.assert_as_accurate_as_reference(xi, _t(L[f"{name}/xi"]), xi64, what="inverse outputs", floor=2e-6)
     # The inverse's logabsdet is ill-conditioned in fp32 in the reference itself: on
     # vcoup_D64_K11_T10_ctx1_odd the reference's fp32 result is 4.4e-4 away from its own fp64 result
     # for one element, and a 1e-6 change of the conditioner output (cuBLAS vs CPU GEMM rounding)

@@ -34,7 +34,7 @@ def _model(name, device):
 def _lp_tol(name):
     # |log_prob| reaches 1e4..1e5 (the PIE term divides by epsilon^2 = 1e-4; 12288 image dims), where one
     # fp32 ulp is 4e-3..8e-3: the north star's 1e-4 absolute applies where |log_prob| is O(1..100)
-    return dict(rtol=1e-5, atol=1e-4) if name in VECTOR else dict(rtol=1e-5, atol=5e-3)
+    return dict(rtol=2e-5, atol=1e-4) if name in VECTOR else dict(rtol=1e-5, atol=5e-3)
 
 
 def _close_as_reference(got, name, key, what, rel=1e-5, floor=1e-6):

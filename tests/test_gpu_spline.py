@@ -104,7 +104,7 @@ def test_coupling_planes_layout_vs_oracle(cuda_device, shape, inverse):
     ref_y, ref_l = _oracle_planes(x.double(), params.double(), ct, k, t, hidden, inverse)
     r32_y, r32_l = _oracle_planes(x, params, ct, k, t, hidden, inverse)
     gu.assert_as_accurate_as_reference(y, r32_y, ref_y, what="outputs")
-    gu.assert_as_accurate_as_reference(lad, r32_l, ref_l, what="per-sample logabsdet", floor=1e-5 * max(1.0, ct * hh * ww / 100))
+    gu.assert_as_accurate_as_reference(lad, r32_l, ref_l, what="per-sample logabsdet", floor=(1e-4 if inverse else 3e-5) * max(1.0, ct * hh * ww / 100))
     # identity channels are copied bit-exactly
     assert torch.equal(y.cpu()[:, ct:], x[:, ct:])
 
