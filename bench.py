@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--math", default=None, choices=[None, "fp32", "tf32"], help="conditioner GEMM math (default: fp32 parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a captured CUDA graph (N=1)")
     return ap.parse_args()
 
 
@@ -232,6 +233,40 @@ def run_b200(args):
             reducer.finish()
         return loss
 
+    # ---- CUDA graph of the whole step (forward + backward), single GPU: ~4900 launches become one replay ----
+    graph = None
+    static_x = static_c = static_loss = None
+    if world == 1 and not args.no_graph:
+        try:
+            static_x, static_c = dev_pool[0][0].clone(), dev_pool[0][1].clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step(static_x, static_c)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(static_x, static_c)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:  # capture is an optimisation: report and fall back to eager launches
+            print(f"[bench] CUDA graph capture failed, running eagerly: {type(exc).__name__}: {str(exc)[:200]}", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(x, c, on_device):
+        """One step on batch (x, c).  With a graph the batch is copied into the graph's static inputs
+        (device->device for resident data, host->device for the end-to-end arm) and the graph replayed."""
+        if graph is None:
+            return step(x, c)
+        static_x.copy_(x, non_blocking=True)
+        static_c.copy_(c, non_blocking=True)
+        graph.replay()
+        return static_loss
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
@@ -246,14 +281,16 @@ def run_b200(args):
         for i in range(n_steps):
             if host_io:
                 xh, ch = pool[i % len(pool)]
-                x, c = xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True)
                 h2d = xh.numel() * 4 + ch.numel() * 4
-                loss = step(x, c)
+                if graph is None:
+                    loss = step(xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True))
+                else:
+                    loss = run_step(xh, ch, False)
                 _ = loss.item()  # device -> host read of the step's result
                 d2h = 4
             else:
                 x, c = dev_pool[i % len(dev_pool)]
-                step(x, c)
+                run_step(x, c, True)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -262,8 +299,11 @@ def run_b200(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms) / 1e3, wall, h2d, d2h
 
+    n_before = cabi.launch_count
+    step(*dev_pool[1 % len(dev_pool)])
+    launches_per_step_eager = cabi.launch_count - n_before  # libmflow_b200 kernels in one step (a graph replays the same)
     for i in range(max(args.warmup, 3)):
-        step(*dev_pool[i % len(dev_pool)])
+        run_step(*dev_pool[i % len(dev_pool)], True)
     # ---- device-resident timing (value) with clocks sampled during the region ----
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
@@ -291,16 +331,35 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        tot_b = sum(v["bytes"] for v in summ.values())
-        tot_ms = sum(v["ms"] for v in summ.values())
-        achieved = tot_b / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else None
-        roof = {"bound": "hbm", "kernel": "rqs_planes_* / rqs_rows_* (fused RQ-spline coupling fwd+inv+bwd, all launches of a step)",
-                "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": (achieved / peak if achieved else None),
-                "traffic": None,
-                "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
-                                   "algorithmic_GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for k, v in summ.items()},
-                "share_of_step": (tot_ms / 2) / (1e3 * secs / args.steps)}
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        tc_peak, tc_src = ((peaks["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained: dense bf16 cuBLAS, kernel timed inside a long step)")
+                           if "bf16_tflops_sustained" in peaks else (1400.0, "fallback"))
+        step_ms = 1e3 * secs / args.steps
+        rqs = {k: v for k, v in summ.items() if k.startswith("rqs_")}
+        conv = {k: v for k, v in summ.items() if k.startswith("conv")}
+
+        def agg(group):
+            return sum(v["bytes"] for v in group.values()), sum(v["ms"] for v in group.values())
+
+        rb, rms = agg(rqs)
+        spline = {"bound": "hbm", "kernel": "rqs_planes_* / rqs_rows_* (fused RQ-spline coupling fwd+inv+bwd, all launches of a step)",
+                  "achieved": rb / (rms * 1e-3) / 1e9 if rms > 0 else None, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                  "traffic": None, "share_of_step": (rms / 2) / step_ms,
+                  "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
+                                     "algorithmic_GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for k, v in rqs.items()}}
+        spline["frac"] = spline["achieved"] / hbm_peak if spline["achieved"] else None
+        if conv:  # the dominant kernel of the step: tcgen05 3xTF32 implicit-GEMM convolution (tensor-bound)
+            cf, cms = agg(conv)  # "bytes" holds useful fp32-equivalent FLOPs for these tags
+            ach = cf / (cms * 1e-3) / 1e12 if cms > 0 else None
+            roof = {"bound": "tensor", "kernel": "conv_tf32x3_kernel (tcgen05 + TMA implicit-GEMM conv, 3xTF32 = 3 tensor passes per useful FLOP; all launches of a step)",
+                    "achieved": ach, "peak": tc_peak, "peak_source": tc_src, "unit": "TFLOP/s", "frac": ach / tc_peak if ach else None,
+                    "traffic": None, "share_of_step": (cms / 2) / step_ms,
+                    "note": "achieved counts useful fp32-equivalent FLOPs; the tensor pipe executes 3x that in TF32 (nominal TF32 peak is half the bf16 peak)",
+                    "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
+                                       "useful_TFLOPs": v["bytes"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None} for k, v in conv.items()},
+                    "secondary": spline}
+        else:
+            roof = spline
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -322,10 +381,12 @@ def run_b200(args):
             "dtype": "f32" if config.conditioner_math == "fp32" else "f32 (tf32 conditioner GEMMs)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * b, "per_gpu_batch": b, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations + spline parameters, several GB) exceeds the 126 MB L2; 4 input batches rotate",
-                       "conditioner": "cuBLAS/cuDNN fp32 library calls (round 1); spline/glue/epilogue kernels: libmflow_b200"},
+                       "conditioner": ("image convolutions forward + data gradient: tcgen05 3xTF32 kernels of libmflow_b200; weight gradients, vector-conditioner GEMMs and the 3840-wide LU layers: cuDNN/cuBLAS fp32"
+                                       if config.conv_tensor_cores else "cuBLAS/cuDNN fp32 library calls")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_secs / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": launches if graph is None else launches_per_step_eager * args.steps,
+            "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
         }))
     if world > 1:
         torch.distributed.barrier()

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float*
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // final reduction over the CTA partials in a fixed order; consecutive threads read consecutive outputs
   for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) {
     float acc = 0.f;
     for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (int64_t)b * n_out + idx);
@@ -332,9 +333,14 @@ static unsigned grid_for(int64_t total, int threads) {
 
 static size_t mix_smem(int C) { return (size_t)(C * C + C * (kMixPix + 1) + C) * sizeof(float); }
 static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
-static int wgrad_grid(int64_t n_pix) {
+static int wgrad_grid(int64_t n_pix, int64_t n_chan) {
+  // as many CTAs as pixel tiles, up to 8 per SM, but the last-arriving CTA sums all partial blocks alone:
+  // keep (CTAs x outputs) below 256K values (1 MB) so that this tail stays at a few microseconds
   int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
-  const int64_t cap = (int64_t)kNumSMs * 8;  // 8 CTAs per SM: the partial blocks stay small (<= 5 MB at C = 48)
+  int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t budget = (256 * 1024) / (n_chan * n_chan + n_chan);
+  if (cap > budget) cap = budget;
+  if (cap < 8) cap = 8;
   return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
@@ -360,7 +366,7 @@ extern "C" MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* d, const floa
 extern "C" MFLOW_API int64_t mflow_chanmix_wgrad_workspace_bytes(const mflow_mix_desc* d) {
   if (!d) return 0;
   const int64_t n_out = d->n_chan * d->n_chan + d->n_chan;
-  return 16 + (int64_t)wgrad_grid(d->n_outer * d->n_inner) * n_out * 4;
+  return 16 + (int64_t)wgrad_grid(d->n_outer * d->n_inner, d->n_chan) * n_out * 4;
 }
 
 extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const float* x, const float* g_y, float* g_mat, float* g_bias,
@@ -369,7 +375,7 @@ extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const floa
   MFLOW_REQUIRE(d->n_chan >= 1 && d->n_chan <= 96, "chanmix_wgrad supports 1..96 channels, got %lld", (long long)d->n_chan);
   const int64_t n_pix = d->n_outer * d->n_inner;
   const int C = (int)d->n_chan;
-  const int grid = wgrad_grid(n_pix);
+  const int grid = wgrad_grid(n_pix, C);
   const int64_t n_out = (int64_t)C * C + C;
   // arrival counter in the first 16 bytes (zero between launches), partial blocks after it
   unsigned int* counter = (unsigned int*)workspace;

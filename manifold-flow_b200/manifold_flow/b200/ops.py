@@ -250,8 +250,13 @@ def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in):
     d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0,
                  n_pad=n_pad, k_pad=k_pad)
     y = torch.empty((b, c_out, h, w), dtype=torch.float32, device=x.device)
+    tok = None
+    if cabi.kernel_timer:  # useful (fp32-equivalent) FLOPs: 2 * pixels * c_in * c_out * taps - NOT the three TF32 passes
+        tok = cabi.kernel_timer.begin(f"conv{kernel}x{kernel}[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out * kernel * kernel)
     check(lib().mflow_conv2d_tf32x3(ctypes.byref(d), ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(residual), ptr(gate), ptr(y), stream()),
           "mflow_conv2d_tf32x3")
+    if tok:
+        cabi.kernel_timer.end(tok)
     cabi.count_launch()
     return y
 
