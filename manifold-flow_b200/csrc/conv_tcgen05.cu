@@ -60,6 +60,8 @@ struct ConvArgs {
   int raw_tx;             // true bytes of one raw box (all 32 channels, all images of the tile)
   int n_tile;             // MMA N extent: 112 when Cout <= 112 (13% less weight traffic and MMA time), else 128
   int n_raw, n_b;         // ring depths: raw boxes, weight tiles
+  int aux_mode;           // 0 none, 1 residual add, 2 ReLU mask (gate)
+  int aux_chunks;         // 32-channel boxes of the aux tile to fetch (0 when aux_mode == 0)
   int debug;              // profiling aid (MFLOW_CONV_DEBUG): bit0 skip MMAs, bit1 skip transform math, bit2 skip stores
 };
 
@@ -70,13 +72,14 @@ __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((_
 
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-                   const __grid_constant__ CUtensorMap map_wlo, const ConvArgs a) {
+                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_aux,
+                   const ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_b = smem;                              // n_b x {B_hi 16 KB, B_lo 16 KB}
   uint8_t* s_raw = s_b + a.n_b * 2 * kStageBytes;   // n_raw x raw box
   __shared__ __align__(8) uint64_t raw_full[kMaxRaw], raw_empty[kMaxRaw], b_full[kMaxStagesB], b_empty[kMaxStagesB],
-      a_full[kStagesA], a_empty[kStagesA], acc_full;
+      a_full[kStagesA], a_empty[kStagesA], acc_full, aux_full;
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,6 +98,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full, 1);
+    mbar_init(&aux_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&s_tmem, kTmemCols);  // [0,128) accumulator, then kStagesA x {A_hi, A_lo} x 32 columns
@@ -119,6 +123,15 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tma_load_3d(s_b + sb * 2 * kStageBytes, &map_whi, &b_full[sb], kb * kBlockK, n0, tap);
           tma_load_3d(s_b + sb * 2 * kStageBytes + kStageBytes, &map_wlo, &b_full[sb], kb * kBlockK, n0, tap);
         }
+      }
+      // Epilogue operand (residual or ReLU mask, shaped like the output): once the last MMA has drained the
+      // weight ring, pull the tile's {W, rows, 32 channels, images} boxes into that memory with TMA - bulk,
+      // asynchronous, 512-byte bursts - instead of 100 dependent 128-byte loads per warp.
+      if (a.aux_chunks) {
+        mbar_wait(&acc_full, 0);
+        mbar_expect_tx(&aux_full, a.aux_chunks * kStageBytes);
+        for (int c = 0; c < a.aux_chunks; ++c)
+          tma_load_4d(s_b + c * kStageBytes, &map_aux, &aux_full, 0, h0, n0 + c * 32, b0);
       }
     }
   } else if (warp == 1) {
@@ -159,6 +172,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int chan_stride = a.box_h * a.box_w;                              // floats between channels in the raw box
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
     const uint32_t t_lane = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+    const int64_t plane = (int64_t)a.H * a.W;
+    const int64_t base = ((int64_t)(b0 + pbl) * a.Cout) * plane + (int64_t)(h0 + phl) * a.W + pw;
     int it = 0;
     for (int kb = 0; kb < a.k_blocks; ++kb) {
       const int rb = kb % a.n_raw;
@@ -194,25 +209,27 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ===== epilogue: TMEM -> registers -> NCHW global, bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const int b = b0 + pbl, h = h0 + phl;
-    const bool ok = b < a.B && !(a.debug & 4);
-    const int64_t plane = (int64_t)a.H * a.W;
-    const int64_t base = ((int64_t)b * a.Cout) * plane + (int64_t)h * a.W + pw;
+    const bool ok = (b0 + pbl) < a.B && !(a.debug & 4);
+    // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
+    const int tile_px = a.rows_per_tile * a.W;
+    const float* aux = reinterpret_cast<const float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
+    if (a.aux_chunks) mbar_wait(&aux_full, 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < kTileN; c0 += 32) {
       if (n0 + c0 >= a.Cout) break;
       float v[32];
       tmem_ld_32x32(t_lane + c0, v);
       if (ok) {
+        const float* auxc = aux + (c0 / 32) * (kStageBytes / 4);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int co = n0 + c0 + j;
           if (co < a.Cout) {
-            float r = v[j] + (a.bias ? a.bias[co] : 0.f);
-            if (a.residual) r += a.residual[base + co * plane];
+            float r = v[j] + (a.bias ? __ldg(a.bias + co) : 0.f);
+            if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
             if (a.relu_out) r = fmaxf(r, 0.f);
-            if (a.gate) r = a.gate[base + co * plane] > 0.f ? r : 0.f;
-            a.y[base + co * plane] = r;
+            if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
+            stg_stream(a.y + base + co * plane, r);
           }
         }
       }
@@ -259,6 +276,7 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
                                              const float* bias, const float* residual, const float* gate, float* y,
                                              void* stream) {
   MFLOW_REQUIRE(d && x && w_hi && w_lo && y, "null pointer");
+  MFLOW_REQUIRE(!(residual && gate), "residual and gate cannot be combined in one call");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
   MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
   MFLOW_REQUIRE(d->height == d->width, "square feature maps only");
@@ -290,7 +308,21 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   if (a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes > two_cta_budget) { a.n_b = 4; a.n_raw = 1; }
   MFLOW_REQUIRE(a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes <= one_cta_budget, "tile does not fit in shared memory");
 
-  CUtensorMap mx, mhi, mlo;
+  a.aux_mode = residual ? 1 : (gate ? 2 : 0);
+  {
+    const int n_here = a.Cout < kTileN ? a.Cout : kTileN;
+    a.aux_chunks = a.aux_mode ? (n_here + 31) / 32 : 0;
+    if (a.aux_chunks * kStageBytes > a.n_b * 2 * kStageBytes) a.n_b = 2;  // the aux tile reuses the weight ring
+    MFLOW_REQUIRE(a.aux_chunks * kStageBytes <= a.n_b * 2 * kStageBytes, "aux tile does not fit in the weight ring");
+  }
+  CUtensorMap mx, mhi, mlo, maux;
+  {  // aux (residual / gate), shaped like y: box {W, rows, 32 channels, images}
+    const float* auxp = residual ? residual : (gate ? gate : y);
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)W, (cuuint32_t)a.rows_per_tile, 32u, (cuuint32_t)a.imgs_per_tile};
+    if (!encode(&maux, auxp, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
+  }
   {  // activations, NCHW: dims (W, H, C, B); box lands in shared memory as [image][channel][row][w]
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
@@ -312,6 +344,6 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
-  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, a);
+  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, maux, a);
   return check_launch("conv_tf32x3_kernel");
 }

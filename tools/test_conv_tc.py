@@ -51,3 +51,25 @@ for name,fn in (('tcgen05 3xTF32',run_tc),('cuDNN fp32 (+relu kernel)',run_cudnn
     for _ in range(10): fn()
     e1.record(); torch.cuda.synchronize(); ms=e0.elapsed_time(e1)/10
     print(f'{name}: {ms*1e3:.0f} us  -> {2*B*1024*900*100/ms/1e9:.1f} TFLOP/s (useful fp32-equivalent)')
+res=torch.randn(B,100,32,32,device=dev); gate=torch.randn(B,100,32,32,device=dev)
+def run_v(r,g,relu):
+    d.relu_in=int(relu)
+    check(lib().mflow_conv2d_tf32x3(ctypes.byref(d),ptr(x),ptr(hi),ptr(lo),ptr(b),ptr(r),ptr(g),ptr(y),stream()),'conv')
+for name,(r,g,relu) in (('plain',(None,None,True)),('+residual',(res,None,True)),('+gate (dgrad)',(None,gate,False))):
+    for _ in range(3): run_v(r,g,relu)
+    torch.cuda.synchronize(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): run_v(r,g,relu)
+    e1.record(); torch.cuda.synchronize(); print(f'variant {name}: {e0.elapsed_time(e1)/10*1e3:.0f} us')
+# cold-cache variant: rotate over 6 different input tensors (630 MB) so x never sits in L2
+xs=[torch.randn(B,100,32,32,device=dev) for _ in range(6)]
+i=[0]
+def run_cold():
+    i[0]+=1
+    check(lib().mflow_conv2d_tf32x3(ctypes.byref(d),ptr(xs[i[0]%6]),ptr(hi),ptr(lo),ptr(b),None,None,ptr(y),stream()),'conv')
+d.relu_in=1
+for _ in range(3): run_cold()
+torch.cuda.synchronize(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(12): run_cold()
+e1.record(); torch.cuda.synchronize(); print(f'variant cold inputs: {e0.elapsed_time(e1)/12*1e3:.0f} us')
