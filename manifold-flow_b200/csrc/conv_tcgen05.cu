@@ -73,7 +73,7 @@ __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((_
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_aux,
-                   const ConvArgs a) {
+                   const __grid_constant__ CUtensorMap map_y, const ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_b = smem;                              // n_b x {B_hi 16 KB, B_lo 16 KB}
@@ -209,7 +209,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ===== epilogue: TMEM -> registers -> NCHW global, bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const bool ok = (b0 + pbl) < a.B && !(a.debug & 4);
+    (void)plane; (void)base;
     // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
     const int tile_px = a.rows_per_tile * a.W;
     const float* aux = reinterpret_cast<const float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
@@ -219,21 +219,26 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (n0 + c0 >= a.Cout) break;
       float v[32];
       tmem_ld_32x32(t_lane + c0, v);
-      if (ok) {
-        const float* auxc = aux + (c0 / 32) * (kStageBytes / 4);
+      // the finished chunk overwrites its own slot of the staging area (same [image][channel][row][w] layout
+      // as the aux boxes) and leaves as ONE asynchronous TMA tile store; channels >= Cout are clipped by TMA
+      float* auxc = const_cast<float*>(aux) + (c0 / 32) * (kStageBytes / 4);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int co = n0 + c0 + j;
-          if (co < a.Cout) {
-            float r = v[j] + (a.bias ? __ldg(a.bias + co) : 0.f);
-            if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
-            if (a.relu_out) r = fmaxf(r, 0.f);
-            if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
-            stg_stream(a.y + base + co * plane, r);
-          }
-        }
+      for (int j = 0; j < 32; ++j) {
+        const int co = n0 + c0 + j;
+        float r = v[j] + ((a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f);
+        if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
+        if (a.relu_out) r = fmaxf(r, 0.f);
+        if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
+        auxc[j * tile_px] = r;
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 128 && !(a.debug & 4)) {
+        tma_store_4d(&map_y, reinterpret_cast<const float*>(s_b) + (c0 / 32) * (kStageBytes / 4), 0, h0, n0 + c0, b0);
+        tma_store_commit();
       }
     }
+    if (threadIdx.x == 128) tma_store_wait<0>();  // shared memory must stay valid until the stores have read it
   }
   tc_fence_before();
   __syncthreads();
@@ -312,10 +317,17 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   {
     const int n_here = a.Cout < kTileN ? a.Cout : kTileN;
     a.aux_chunks = a.aux_mode ? (n_here + 31) / 32 : 0;
-    if (a.aux_chunks * kStageBytes > a.n_b * 2 * kStageBytes) a.n_b = 2;  // the aux tile reuses the weight ring
+    const int out_chunks = (n_here + 31) / 32;  // the output tile is staged in the weight ring as well
+    if (out_chunks * kStageBytes > a.n_b * 2 * kStageBytes) a.n_b = 2;
     MFLOW_REQUIRE(a.aux_chunks * kStageBytes <= a.n_b * 2 * kStageBytes, "aux tile does not fit in the weight ring");
   }
-  CUtensorMap mx, mhi, mlo, maux;
+  CUtensorMap mx, mhi, mlo, maux, my;
+  {  // output, NCHW: box {W, rows, 32 channels, images}
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)W, (cuuint32_t)a.rows_per_tile, 32u, (cuuint32_t)a.imgs_per_tile};
+    if (!encode(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
+  }
   {  // aux (residual / gate), shaped like y: box {W, rows, 32 channels, images}
     const float* auxp = residual ? residual : (gate ? gate : y);
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
@@ -344,6 +356,6 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
-  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, maux, a);
+  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, maux, my, a);
   return check_launch("conv_tf32x3_kernel");
 }
