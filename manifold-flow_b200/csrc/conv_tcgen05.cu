@@ -12,16 +12,17 @@
 //   padding of the convolution and of channels 100..127 is TMA's out-of-bounds fill.
 // * fp32 parity on TF32 tensor cores by the 3xTF32 split: a = a_hi + a_lo with a_hi the TF32 truncation;
 //   D += A_hi B_hi + A_lo B_hi + A_hi B_lo.  Weights are split once per optimizer step on the host side of
-//   the ABI.  Activations are handled by the CTA's four transform warps between TMA arrival and the MMA:
-//   one thread per pixel reads its 32 channels (conflict-free), applies the pre-activation ReLU, splits,
-//   and stores A_hi / A_lo straight into TENSOR MEMORY (tcgen05.st, thread = TMEM lane = pixel), from
+//   the ABI.  Activations are handled by the CTA's eight transform warps between TMA arrival and the MMA:
+//   two threads per pixel (16 channels each) read their channels (conflict-free), apply the
+//   pre-activation ReLU, split, and store A_hi / A_lo straight into TENSOR MEMORY (tcgen05.st, TMEM lane = pixel), from
 //   where the MMA reads its A operand: the NCHW -> [pixel][channel] transposition costs no extra pass
 //   and the activation operand never touches shared memory again.
 // * Accumulator: 128 lanes x 128 columns of TMEM; epilogue tcgen05.ld 32x32b gives every thread one pixel
 //   row, so for a fixed output channel a warp stores 32 consecutive pixels (coalesced NCHW writes) with
 //   bias / residual / ReLU / ReLU-mask fused.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 4-7 = transform, then
-//   epilogue.  Hand-offs through mbarrier rings; tcgen05.commit releases slots.  Two CTAs share an SM so
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = transform, then
+//   epilogue (a warp may only touch the TMEM lane quadrant warp_id % 4, so every quadrant has two warps:
+//   they split the channels of a step and the column chunks of the epilogue).  Hand-offs through mbarrier rings; tcgen05.commit releases slots.  Two CTAs share an SM so
 //   that one CTA's prologue / epilogue overlaps the other's main loop.
 #include <stdarg.h>
 #include <stdlib.h>
@@ -37,7 +38,8 @@ constexpr int kTileM = 128;   // pixels per CTA tile
 constexpr int kTileN = 128;   // accumulator columns (output channels per CTA tile, N extent <= 128)
 constexpr int kBlockK = 32;   // input channels per pipeline step
 constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one weight operand tile (hi or lo)
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 320;   // 2 control warps + 8 transform / epilogue warps
+constexpr int kXfWarps = 8;
 constexpr int kStagesA = 2;       // activation operand stages in TMEM
 constexpr int kTmemCols = 256;    // 128 accumulator columns + kStagesA x (A_hi 32 + A_lo 32)
 constexpr int kMaxStagesB = 4;
@@ -94,9 +96,9 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_whi);
     prefetch_tensormap(&map_wlo);
-    for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
+    for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kXfWarps); }
     for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], kXfWarps); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_init(&aux_full, 1);
     fence_barrier_init();
@@ -164,19 +166,19 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       umma_commit(&acc_full);
     }
-  } else if (warp >= 4) {
-    // ===== activation transform: thread = pixel = TMEM lane =====
-    const int pm = threadIdx.x - 128;
+  } else {
+    // ===== activation transform: TMEM lane = pixel; the two warps of a lane quadrant split the channels =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int pm = quad * 32 + lane;
     const int pw = pm % a.W, pg = pm / a.W;
     const int phl = pg % a.rows_per_tile, pbl = pg / a.rows_per_tile;
     const int chan_stride = a.box_h * a.box_w;                              // floats between channels in the raw box
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
-    const uint32_t t_lane = tmem + ((uint32_t)((warp - 4) * 32) << 16);
-    const int64_t plane = (int64_t)a.H * a.W;
-    const int64_t base = ((int64_t)(b0 + pbl) * a.Cout) * plane + (int64_t)(h0 + phl) * a.W + pw;
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     int it = 0;
     for (int kb = 0; kb < a.k_blocks; ++kb) {
       const int rb = kb % a.n_raw;
+      const int nch = (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
       mbar_wait(&raw_full[rb], (kb / a.n_raw) & 1);
       const float* raw = reinterpret_cast<const float*>(s_raw + rb * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, ++it) {
@@ -184,44 +186,52 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int sa = it % kStagesA;
         mbar_wait(&a_empty[sa], ((it / kStagesA) & 1) ^ 1);
         tc_fence_after();
-        // gather the pixel's 32 channels of this tap, optional ReLU, TF32 hi / lo split, and store both
-        // parts into this thread's TMEM lane (32 columns each)
+        // gather this thread's channels of the tap, optional ReLU, TF32 hi / lo split, and store both parts
+        // into the pixel's TMEM lane (A_hi columns [0,32), A_lo columns [32,64) of the stage)
         const float* src = raw + (pad ? dy * a.box_w + dx + 3 : 0);
+        const uint32_t t_a = t_lane + kTileN + sa * 2 * kBlockK;
         if (!(a.debug & 2)) {
-          float hi[32], lo[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float v = src[c * chan_stride];
-            if (a.relu_in) v = fmaxf(v, 0.f);
-            hi[c] = tf32_trunc(v);
-            lo[c] = tf32_round(v - hi[c]);
+          for (int g = 0; g < 2; ++g) {
+            const int c0 = half * 16 + g * 8;
+            if (c0 < nch) {
+              float hi[8], lo[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                float v = src[(c0 + c) * chan_stride];
+                if (a.relu_in) v = fmaxf(v, 0.f);
+                hi[c] = tf32_trunc(v);
+                lo[c] = tf32_round(v - hi[c]);
+              }
+              tmem_st_32x8(t_a + c0, hi);
+              tmem_st_32x8(t_a + kBlockK + c0, lo);
+            }
           }
-          const uint32_t t_a = t_lane + kTileN + sa * 2 * kBlockK;
-          tmem_st_32x32(t_a, hi);
-          tmem_st_32x32(t_a + kBlockK, lo);
           tmem_st_wait();
         }
         tc_fence_before();
-        mbar_arrive(&a_full[sa]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
       }
-      mbar_arrive(&raw_empty[rb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[rb]);
     }
-    // ===== epilogue: TMEM -> registers -> NCHW global, bias / residual / ReLU / mask fused =====
+    // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    (void)plane; (void)base;
     // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
     const int tile_px = a.rows_per_tile * a.W;
-    const float* aux = reinterpret_cast<const float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
+    float* stage = reinterpret_cast<float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
     if (a.aux_chunks) mbar_wait(&aux_full, 0);
+    const bool issuer = (warp == 2 + 4 * half) && lane == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kTileN; c0 += 32) {
+    for (int c0 = half * 32; c0 < kTileN; c0 += 64) {   // 32-column chunks alternate between the two halves
       if (n0 + c0 >= a.Cout) break;
       float v[32];
       tmem_ld_32x32(t_lane + c0, v);
       // the finished chunk overwrites its own slot of the staging area (same [image][channel][row][w] layout
       // as the aux boxes) and leaves as ONE asynchronous TMA tile store; channels >= Cout are clipped by TMA
-      float* auxc = const_cast<float*>(aux) + (c0 / 32) * (kStageBytes / 4);
+      float* auxc = stage + (c0 / 32) * (kStageBytes / 4);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int co = n0 + c0 + j;
@@ -232,13 +242,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         auxc[j * tile_px] = r;
       }
       fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 128 && !(a.debug & 4)) {
+      if (half) named_bar_sync<2>(128); else named_bar_sync<1>(128);
+      if (issuer && !(a.debug & 4)) {
         tma_store_4d(&map_y, reinterpret_cast<const float*>(s_b) + (c0 / 32) * (kStageBytes / 4), 0, h0, n0 + c0, b0);
         tma_store_commit();
       }
     }
-    if (threadIdx.x == 128) tma_store_wait<0>();  // shared memory must stay valid until the stores have read it
+    if (issuer) tma_store_wait<0>();  // shared memory must stay valid until the stores have read it
   }
   tc_fence_before();
   __syncthreads();
