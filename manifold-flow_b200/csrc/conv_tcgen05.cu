@@ -72,12 +72,21 @@ __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__
 // split is pre-rounded to keep the truncation from biasing the sum
 __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
+// ring cursor without divisions: slot index + phase parity
+struct Ring {
+  int slot, phase, n;
+  __device__ __forceinline__ Ring(int depth) : slot(0), phase(0), n(depth) {}
+  __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } }
+};
+
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_aux,
                    const __grid_constant__ CUtensorMap map_y, const ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through uintptr_t makes the
+  // compiler forget the address space and emit generic loads for the activation gather)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_b = smem;                              // n_b x {B_hi 16 KB, B_lo 16 KB}
   uint8_t* s_raw = s_b + a.n_b * 2 * kStageBytes;   // n_raw x raw box
   __shared__ __align__(8) uint64_t raw_full[kMaxRaw], raw_empty[kMaxRaw], b_full[kMaxStagesB], b_empty[kMaxStagesB],
@@ -98,7 +107,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     prefetch_tensormap(&map_wlo);
     for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kXfWarps); }
     for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], kXfWarps); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], kXfWarps / 2); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_init(&aux_full, 1);
     fence_barrier_init();
@@ -111,19 +120,17 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      for (int kb = 0; kb < a.k_blocks; ++kb) {
-        const int rb = kb % a.n_raw;
-        mbar_wait(&raw_empty[rb], ((kb / a.n_raw) & 1) ^ 1);
-        mbar_expect_tx(&raw_full[rb], a.raw_tx);
-        tma_load_4d(s_raw + rb * a.raw_bytes, &map_x, &raw_full[rb], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
-        for (int tap = 0; tap < a.taps; ++tap, ++it) {
-          const int sb = it % a.n_b;
-          mbar_wait(&b_empty[sb], ((it / a.n_b) & 1) ^ 1);
-          mbar_expect_tx(&b_full[sb], 2 * a.n_tile * kBlockK * 4);
-          tma_load_3d(s_b + sb * 2 * kStageBytes, &map_whi, &b_full[sb], kb * kBlockK, n0, tap);
-          tma_load_3d(s_b + sb * 2 * kStageBytes + kStageBytes, &map_wlo, &b_full[sb], kb * kBlockK, n0, tap);
+    if (elect_one()) {
+      Ring rb(a.n_raw), sb(a.n_b);
+      for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
+        mbar_wait(&raw_empty[rb.slot], rb.phase ^ 1);
+        mbar_expect_tx(&raw_full[rb.slot], a.raw_tx);
+        tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+        for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
+          mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
+          mbar_expect_tx(&b_full[sb.slot], 2 * a.n_tile * kBlockK * 4);
+          tma_load_3d(s_b + sb.slot * 2 * kStageBytes, &map_whi, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          tma_load_3d(s_b + sb.slot * 2 * kStageBytes + kStageBytes, &map_wlo, &b_full[sb.slot], kb * kBlockK, n0, tap);
         }
       }
       // Epilogue operand (residual or ReLU mask, shaped like the output): once the last MMA has drained the
@@ -138,36 +145,45 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    // elect.sync (not lane == 0): the compiler then issues the tcgen05 instructions back to back instead of
+    // wrapping each one in a warp-election loop (the MMAs here are only 56 cycles long)
+    if (elect_one()) {
       const uint32_t idesc = idesc_tf32(kTileM, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
-      uint32_t accumulate = 0;
-      int it = 0;
+      Ring sb(a.n_b), sa(kStagesA);
       for (int kb = 0; kb < a.k_blocks; ++kb) {
         const int valid = min(kBlockK, a.Cin - kb * kBlockK);
         const int ksteps = (a.debug & 1) ? 0 : (valid + 7) / 8;
-        for (int tap = 0; tap < a.taps; ++tap, ++it) {
-          const int sa = it % kStagesA, sb = it % a.n_b;
-          mbar_wait(&a_full[sa], (it / kStagesA) & 1);
-          mbar_wait(&b_full[sb], (it / a.n_b) & 1);
+        for (int tap = 0; tap < a.taps; ++tap, sb.next(), sa.next()) {
+          const bool first = kb == 0 && tap == 0;
+          mbar_wait(&a_full[sa.slot], sa.phase);
+          mbar_wait(&b_full[sb.slot], sb.phase);
           tc_fence_after();
-          const uint32_t ahi = tmem + kTileN + sa * 2 * kBlockK, alo = ahi + kBlockK;
-          const uint32_t bhi = smem_u32(s_b + sb * 2 * kStageBytes), blo = bhi + kStageBytes;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes further along each row
-            const uint64_t d_bhi = smem_desc(bhi + kk * 32, 16, 1024, 2), d_blo = smem_desc(blo + kk * 32, 16, 1024, 2);
-            umma_tf32_ts(tmem, ahi + kk * 8, d_bhi, idesc, accumulate);
-            umma_tf32_ts(tmem, alo + kk * 8, d_bhi, idesc, 1);
-            umma_tf32_ts(tmem, ahi + kk * 8, d_blo, idesc, 1);
-            accumulate = 1;
+          const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kBlockK, alo = ahi + kBlockK;
+          const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * kStageBytes);
+          // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes (2 descriptor units) further along each row
+          const uint64_t d_bhi = smem_desc(bhi, 16, 1024, 2), d_blo = smem_desc(bhi + kStageBytes, 16, 1024, 2);
+          if (ksteps == 4) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+              umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
+              umma_tf32_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
+            }
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk) {
+              umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+              umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
+              umma_tf32_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
+            }
           }
-          umma_commit(&a_empty[sa]);  // slots are free again once these MMAs have read them
-          umma_commit(&b_empty[sb]);
+          umma_commit(&a_empty[sa.slot]);  // slots are free again once these MMAs have read them
+          umma_commit(&b_empty[sb.slot]);
         }
       }
       umma_commit(&acc_full);
     }
   } else {
-    // ===== activation transform: TMEM lane = pixel; the two warps of a lane quadrant split the channels =====
+    // ===== activation transform: TMEM lane = pixel; the two warps of a lane quadrant alternate pipeline steps =====
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int pm = quad * 32 + lane;
     const int pw = pm % a.W, pg = pm / a.W;
@@ -175,25 +191,27 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int chan_stride = a.box_h * a.box_w;                              // floats between channels in the raw box
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    int it = 0;
-    for (int kb = 0; kb < a.k_blocks; ++kb) {
-      const int rb = kb % a.n_raw;
+    // The halves alternate pipeline steps (half h owns TMEM stage h): two steps are in flight in different
+    // warps, so one warp's gather / split / tcgen05.st latency hides behind the other's.
+    const uint32_t t_a = t_lane + kTileN + half * 2 * kBlockK;
+    Ring rb(a.n_raw);
+    int step = 0, pa = 0;   // step parity; phase of this half's stage
+    for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
       const int nch = (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
-      mbar_wait(&raw_full[rb], (kb / a.n_raw) & 1);
-      const float* raw = reinterpret_cast<const float*>(s_raw + rb * a.raw_bytes) + raw_base;
-      for (int tap = 0; tap < a.taps; ++tap, ++it) {
-        const int dy = pad ? tap / 3 : 0, dx = pad ? tap % 3 : 0;
-        const int sa = it % kStagesA;
-        mbar_wait(&a_empty[sa], ((it / kStagesA) & 1) ^ 1);
+      mbar_wait(&raw_full[rb.slot], rb.phase);
+      const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
+      for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
+        if (step != half) continue;
+        const float* src = raw + (pad ? (tap / 3) * a.box_w + tap % 3 + 3 : 0);
+        mbar_wait(&a_empty[half], pa ^ 1);
+        pa ^= 1;
         tc_fence_after();
-        // gather this thread's channels of the tap, optional ReLU, TF32 hi / lo split, and store both parts
+        // gather the pixel's channels of the tap, optional ReLU, TF32 hi / lo split, and store both parts
         // into the pixel's TMEM lane (A_hi columns [0,32), A_lo columns [32,64) of the stage)
-        const float* src = raw + (pad ? dy * a.box_w + dx + 3 : 0);
-        const uint32_t t_a = t_lane + kTileN + sa * 2 * kBlockK;
         if (!(a.debug & 2)) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int c0 = half * 16 + g * 8;
+          for (int g = 0; g < 4; ++g) {
+            const int c0 = g * 8;
             if (c0 < nch) {
               float hi[8], lo[8];
 #pragma unroll
@@ -211,10 +229,10 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[sa]);
+        if (lane == 0) mbar_arrive(&a_full[half]);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rb]);
+      if (lane == 0) mbar_arrive(&raw_empty[rb.slot]);   // this warp's reads of the box are program-ordered before
     }
     // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);

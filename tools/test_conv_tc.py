@@ -5,6 +5,7 @@ for p in ('manifold-flow_b200','oracle','tests',''): sys.path.insert(0, os.path.
 import torch, torch.nn.functional as F
 from manifold_flow.b200 import cabi
 from manifold_flow.b200.cabi import ConvDesc, lib, ptr, stream, check
+if os.environ.get('MFLOW_LIB'): cabi._LIB_PATH = os.environ['MFLOW_LIB']  # tooling only: time another build of the library
 dev=torch.device('cuda')
 def prep(w):
     co,ci,kh,kw=w.shape
@@ -22,7 +23,7 @@ def conv_tc(x,w,b=None,res=None,relu_in=False,relu_out=False):
     check(lib().mflow_conv2d_tf32x3(ctypes.byref(d),ptr(x),ptr(hi),ptr(lo),ptr(b),ptr(res),None,ptr(y),stream()),'conv')
     return y
 torch.manual_seed(0)
-cases=[] if os.environ.get('MFLOW_CONV_DEBUG') else [(2,100,100,32,3),(2,100,100,16,3),(4,100,100,8,3),(9,100,100,4,3),(2,6,100,32,1),(3,100,192,32,1),(2,100,384,16,1),(2,48,100,4,1),(1,8,8,32,3)]
+cases=[] if (os.environ.get('MFLOW_CONV_DEBUG') or os.environ.get('MFLOW_CONV_TIMING_ONLY')) else [(2,100,100,32,3),(2,100,100,16,3),(4,100,100,8,3),(9,100,100,4,3),(2,6,100,32,1),(3,100,192,32,1),(2,100,384,16,1),(2,48,100,4,1),(1,8,8,32,3)]
 if len(sys.argv)>1: cases=cases[:int(sys.argv[1])]
 for (B,ci,co,HW,k) in cases:
     x=torch.randn(B,ci,HW,HW,device=dev); w=torch.randn(co,ci,k,k,device=dev)*0.1; b=torch.randn(co,device=dev); r=torch.randn(B,co,HW,HW,device=dev)
