@@ -131,6 +131,13 @@ MFLOW_API int64_t mflow_chanmix_wgrad_workspace_bytes(const mflow_mix_desc* desc
 MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* desc, const float* x, const float* g_y, float* g_mat,
                         float* g_bias, void* workspace, void* stream);
 
+/* out[c] = sum_{b,i} x[b, c, i] over a contiguous [batch, chan, inner] tensor: the bias gradient of the
+ * conditioner's convolutions (autograd of nn.Conv2d in nn/resnet.py:85-142; ATen sum over dims (0,2,3)).
+ * Deterministic two-pass reduction; workspace: mflow_channel_sum_workspace_bytes() bytes, no initialisation. */
+MFLOW_API int64_t mflow_channel_sum_workspace_bytes(int64_t batch, int64_t chan, int64_t inner);
+MFLOW_API int mflow_channel_sum(const float* x, float* out, int64_t batch, int64_t chan, int64_t inner, void* workspace,
+                      void* stream);
+
 /* 2x2 space-to-depth with a fused scalar affine map: y = squeeze(x) * scale + shift (forward) or
  * y = unsqueeze((x - shift) / scale) (inverse).  SqueezeTransform (transforms/reshape.py:29-57) and
  * AffineScalarTransform (transforms/standard.py:41-57).  x [B, C, H, W] contiguous. */

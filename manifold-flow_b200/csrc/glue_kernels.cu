@@ -389,6 +389,68 @@ extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const floa
   return check_launch("chanmix_wgrad_kernel");
 }
 
+// ---- per-channel sum over [B, C, I] (bias gradient of a convolution) ---------------------------
+// Pass 1: CTA (c, s) adds the images b = s, s + S, ... of channel c (each a contiguous run of I floats) and
+// writes partial[c][s]; pass 2 adds the S partials of a channel in index order.  Deterministic.
+constexpr int kSumThreads = 256;
+__global__ void __launch_bounds__(kSumThreads) channel_sum_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
+                                                                          int B, int C, int I, int S) {
+  __shared__ float red[kSumThreads / 32];
+  const int c = blockIdx.x, s = blockIdx.y;
+  float acc = 0.f;
+  if ((I & 3) == 0) {
+    const int i4n = I >> 2;
+    // threads sweep (image, float4) pairs: consecutive threads read consecutive float4s of one image
+    const int n_img = (B - s + S - 1) / S;
+    for (int j = threadIdx.x; j < n_img * i4n; j += kSumThreads) {
+      const int bi = j / i4n, i4 = j - bi * i4n;
+      const int b = s + bi * S;
+      const float4 v = ldg_stream4(reinterpret_cast<const float4*>(x + ((int64_t)b * C + c) * I) + i4);
+      acc += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    const int n_img = (B - s + S - 1) / S;
+    for (int j = threadIdx.x; j < n_img * I; j += kSumThreads) {
+      const int bi = j / I, i = j - bi * I;
+      acc += x[((int64_t)(s + bi * S) * C + c) * I + i];
+    }
+  }
+  acc = block_sum<kSumThreads>(acc, red);
+  if (threadIdx.x == 0) partial[c * S + s] = acc;
+}
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int C, int S) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += partial[c * S + s];
+  out[c] = acc;
+}
+static int channel_sum_splits(int64_t batch, int64_t chan) {
+  int64_t s = (4 * 148 + chan - 1) / chan;   // about four waves of CTAs
+  if (s > batch) s = batch;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+extern "C" MFLOW_API int64_t mflow_channel_sum_workspace_bytes(int64_t batch, int64_t chan, int64_t inner) {
+  (void)inner;
+  return chan * channel_sum_splits(batch, chan) * (int64_t)sizeof(float);
+}
+extern "C" MFLOW_API int mflow_channel_sum(const float* x, float* out, int64_t batch, int64_t chan, int64_t inner, void* workspace,
+                                           void* stream) {
+  MFLOW_REQUIRE(out && chan >= 1 && batch >= 0 && inner >= 0, "bad arguments");
+  MFLOW_REQUIRE(chan <= 65535 * 32 && batch * chan * inner < ((int64_t)1 << 40), "tensor too large");
+  if (batch == 0 || inner == 0) {
+    return cudaMemsetAsync(out, 0, chan * sizeof(float), (cudaStream_t)stream) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+  }
+  MFLOW_REQUIRE(x && workspace, "null pointer");
+  MFLOW_REQUIRE(batch <= INT32_MAX && inner <= (1 << 24), "extent too large");
+  const int S = channel_sum_splits(batch, chan);
+  dim3 grid((unsigned)chan, (unsigned)S);
+  channel_sum_partial_kernel<<<grid, kSumThreads, 0, (cudaStream_t)stream>>>(x, (float*)workspace, (int)batch, (int)chan, (int)inner, S);
+  channel_sum_final_kernel<<<(unsigned)((chan + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, out, (int)chan, S);
+  return check_launch("channel_sum_kernel");
+}
+
 extern "C" MFLOW_API int mflow_squeeze2x2(const float* x, float* y, int64_t batch, int64_t chan, int64_t height, int64_t width,
                                 int32_t inverse, float scale, float shift, void* stream) {
   MFLOW_REQUIRE(x && y, "null pointer");

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),
     "mflow_chanmix_wgrad_workspace_bytes": (i64, [ctypes.POINTER(MixDesc)]),
     "mflow_chanmix_wgrad": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 6),
+    "mflow_channel_sum_workspace_bytes": (i64, [i64, i64, i64]),
+    "mflow_channel_sum": (ctypes.c_int, [c_f32p, c_f32p, i64, i64, i64, c_f32p, c_f32p]),
     "mflow_squeeze2x2": (ctypes.c_int, [c_f32p, c_f32p, i64, i64, i64, i64, i32, f32, f32, c_f32p]),
     "mflow_affine_scalar": (ctypes.c_int, [c_f32p, c_f32p, i64, f32, f32, i32, c_f32p]),
     "mflow_permute_rows": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, c_f32p]),

@@ -290,8 +290,21 @@ class _ConvTC(torch.autograd.Function):
             gw = torch.ops.aten.convolution_backward(g, xin, weight, None, [1, 1], [kernel // 2] * 2, [1, 1], False, [0, 0], 1,
                                                      [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(dim=(0, 2, 3))
+            gb = channel_sum(g)
         return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None
+
+
+def channel_sum(x):
+    """sum over all dims but 1 of a contiguous [B, C, ...] tensor (bias gradient of a convolution)."""
+    require_cuda(x)
+    x = _c(x)
+    batch, chan = x.shape[0], x.shape[1]
+    inner = x[0, 0].numel() if batch and chan else 0
+    out = torch.empty(chan, dtype=torch.float32, device=x.device)
+    ws = cabi.workspace("channel_sum", lib().mflow_channel_sum_workspace_bytes(batch, chan, inner), x.device)
+    check(lib().mflow_channel_sum(ptr(x), ptr(out), batch, chan, inner, ptr(ws), stream()), "mflow_channel_sum")
+    cabi.count_launch(2)
+    return out
 
 
 def conv_tc(x, weight, bias=None, residual=None, relu_in=False):

@@ -82,3 +82,21 @@ def test_unsupported_shapes_fall_back_loudly(cuda_device):
     assert not ops.conv_tc_supported(x, w)
     with pytest.raises(ValueError):
         ops.conv_tc(x, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(256, 100, 32, 32), (7, 100, 16, 16), (5, 192, 8, 8), (64, 48, 4, 4), (3, 5, 7), (1, 1, 1, 1), (0, 4, 2, 2),
+                                   (300, 3, 33)])
+def test_channel_sum_matches_fp64_sum(cuda_device, shape):
+    """mflow_channel_sum (bias gradient of the conditioner convolutions) against an fp64 sum; deterministic."""
+    from manifold_flow.b200 import ops
+
+    torch.manual_seed(5)
+    x = torch.randn(*shape, device=cuda_device) + 0.3
+    got = ops.channel_sum(x)
+    dims = [d for d in range(x.dim()) if d != 1]
+    want = x.double().sum(dim=dims)
+    scale = x.double().abs().sum(dim=dims).clamp_min(1.0)
+    assert got.shape == want.shape
+    assert ((got.double() - want).abs() / scale).max().item() < 1e-6 if got.numel() else True
+    assert torch.equal(got, ops.channel_sum(x))
