@@ -180,6 +180,17 @@ typedef struct {
 MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
                         const float* bias, const float* residual, const float* gate, float* y, void* stream);
 
+/* Weight gradient of the same convolutions (autograd of nn.Conv2d in nn/resnet.py:85-142; the reference runs
+ * cuDNN / cuBLAS fp32 wgrad kernels):
+ *   g_w[co, ci, ky, kx] = sum_{b,h,w} g_y[b, co, h, w] * (relu_in ? relu(x) : x)[b, ci, h + ky - 1, w + kx - 1]
+ * written in the reference's weight layout [c_out, c_in, kernel, kernel].  3xTF32 on tcgen05 with the pixels as the
+ * reduction dimension, split over CTAs and reduced deterministically.  height == width in {8, 16, 32};
+ * kernel == 3 needs c_out <= 112.  desc->relu_out, n_pad, k_pad are ignored.
+ * workspace: mflow_conv2d_wgrad_workspace_bytes(desc) bytes, no initialisation needed. */
+MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* desc);
+MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* desc, const float* x, const float* g_y, float* g_w,
+                              void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Likelihood epilogues.
  * ---------------------------------------------------------------------------------- */

@@ -1,0 +1,348 @@
+// Weight gradient of the conditioner convolutions on the 5th-generation tensor cores.
+//
+//   g_w[co, ci, ky, kx] = sum_{b, h, w} g_y[b, co, h, w] * relu?(x)[b, ci, h + ky - 1, w + kx - 1]
+//
+// (autograd of nn.Conv2d 3x3 pad 1 / 1x1 in ConvResidualNet, reference manifold_flow/nn/resnet.py:85-142), as a
+// GEMM whose reduction dimension K is the PIXELS of the batch:
+//
+//   D_tap[ci, co] += P_tap[ci, 32 px] * Q[co, 32 px]^T        per 32-pixel block, per tap
+//
+// * Both tensors are NCHW, i.e. already "K-major" (the pixels of one channel of one image are contiguous): no
+//   im2col, no transposition pass.  Q (the output gradient) lands in shared memory as a 128-byte-swizzled
+//   K-major tile straight from one TMA load and is split in place into its TF32 hi / lo parts.
+// * P (the activations) is the operand that needs the 3x3 shifts.  It goes to TENSOR MEMORY with lane = input
+//   channel and columns = the 32 pixels of the block: the transform thread of a channel holds the block's
+//   image rows INCLUDING the left / right halo in registers and stores, per horizontal tap, the window
+//   shifted by that tap (a TMEM operand address must be a multiple of 4 columns, so the shift cannot be a
+//   column offset of the MMA - measured: "misaligned address").  The vertical tap is the row the TMA box is
+//   taken from; out-of-bounds rows and columns are TMA zero fill = the convolution's padding.  ReLU and the
+//   hi / lo split happen on the way.
+// * 3xTF32: D += P_hi Q_hi + P_lo Q_hi + P_hi Q_lo with fp32 accumulation in TMEM (fp32-level accuracy).
+// * Split-K: CTA (ks, dy) reduces its share of the pixel blocks for the three taps of kernel row dy into
+//   three TMEM accumulators and writes a partial [tap][ci][co]; a second kernel adds the partials in index
+//   order (deterministic) and writes g_w in the reference's [co][ci][ky][kx] layout.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 P transform (two sets of four alternate
+//   pixel blocks, one TMEM stage each) and epilogue, warps 10-13 Q split.
+#include <stdlib.h>
+
+#include "mflow_common.cuh"
+#include "tc_ptx.cuh"
+#include "tma_encode.cuh"
+
+namespace mflow {
+
+using namespace ptx;
+
+constexpr int kWgThreads = 32 * 14;
+constexpr int kWgBlockPx = 32;                 // pixels per K block
+constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
+constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
+constexpr int kWgRawSlots = 3, kWgQSlots = 3;
+
+struct WgradArgs {
+  float* partial;   // [ks][taps][Cin][Cout]
+  int B, Cin, Cout, H, W;
+  int taps;         // 9 or 1
+  int relu_in;
+  int rows;         // image rows per 32-pixel block (32 / W)
+  int box_w;        // raw activation box width: W + 8 (3x3, starts 4 pixels left: TMA needs 16-byte aligned starts) or W
+  int raw_bytes;    // one raw activation box [128 ci][rows][box_w] fp32
+  int n_tile;       // MMA N extent (output channels of this launch's q tile, multiple of 16, <= 128)
+  int blocks_per_img;  // H * W / 32
+  int n_blocks;     // B * blocks_per_img
+  int n_dy;         // 3 (3x3) or 1
+  int tmem_cols;
+};
+
+__device__ __forceinline__ float wg_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ float wg_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+struct WgRing {
+  int slot, phase, n;
+  __device__ __forceinline__ WgRing(int depth) : slot(0), phase(0), n(depth) {}
+  __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } }
+};
+
+template <int kW, int kTaps>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_q = smem;                                   // kWgQSlots x {Q_hi 16 KB, Q_lo 16 KB}
+  uint8_t* s_p = s_q + kWgQSlots * 2 * kWgQBytes;        // kWgRawSlots x raw activation box
+  __shared__ __align__(8) uint64_t rawp_full[kWgRawSlots], rawp_empty[kWgRawSlots], qraw_full[kWgQSlots], q_full[kWgQSlots],
+      q_empty[kWgQSlots], p_full[2], p_empty[2], acc_full;
+  __shared__ uint32_t s_tmem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x = K split, blockIdx.y = kernel row dy, blockIdx.z = (q tile, p tile)
+  const int ks = blockIdx.x, n_ks = gridDim.x;
+  const int dy = blockIdx.y;
+  const int p_tiles = (a.Cin + 127) / 128;
+  const int p0 = (blockIdx.z % p_tiles) * 128, q0 = (blockIdx.z / p_tiles) * 128;
+  const int per = a.n_blocks / n_ks, extra = a.n_blocks % n_ks;
+  const int blk0 = ks * per + min(ks, extra), n_my = per + (ks < extra ? 1 : 0);
+  constexpr int taps_here = kTaps == 9 ? 3 : 1;
+  constexpr int pad = kTaps == 9 ? 1 : 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_g);
+    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], 8); }
+    for (int i = 0; i < kWgQSlots; ++i) { mbar_init(&qraw_full[i], 1); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&s_tmem, a.tmem_cols);  // taps_here x n_tile accumulator columns, then 2 x {P_hi, P_lo} x 32
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tmem_p = tmem + taps_here * a.n_tile;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      WgRing rp(kWgRawSlots), rq(kWgQSlots);
+      for (int i = 0; i < n_my; ++i, rp.next(), rq.next()) {
+        const int blk = blk0 + i;
+        const int b = blk / a.blocks_per_img, r = blk - b * a.blocks_per_img;   // image, 32-pixel block in it
+        const int h0 = r * a.rows;
+        mbar_wait(&rawp_empty[rp.slot], rp.phase ^ 1);
+        mbar_expect_tx(&rawp_full[rp.slot], a.raw_bytes);
+        tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], pad ? -4 : 0, h0 + (pad ? dy - 1 : 0), p0, b);
+        mbar_wait(&q_empty[rq.slot], rq.phase ^ 1);
+        mbar_expect_tx(&qraw_full[rq.slot], a.n_tile * kWgBlockPx * 4);
+        tma_load_3d(s_q + rq.slot * 2 * kWgQBytes, &map_g, &qraw_full[rq.slot], r * kWgBlockPx, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc = idesc_tf32(128, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      WgRing rq(kWgQSlots);
+      int sp = 0, pp = 0;   // P stage and its phase; one stage per (block, tap) work item
+      for (int i = 0; i < n_my; ++i, rq.next()) {
+        mbar_wait(&q_full[rq.slot], rq.phase);
+        const uint32_t qhi = smem_u32(s_q + rq.slot * 2 * kWgQBytes);
+        const uint64_t d_qhi = smem_desc(qhi, 16, 1024, 2), d_qlo = smem_desc(qhi + kWgQBytes, 16, 1024, 2);
+#pragma unroll
+        for (int t = 0; t < taps_here; ++t) {
+          mbar_wait(&p_full[sp], pp);
+          tc_fence_after();
+          const uint32_t acc = tmem + t * a.n_tile;
+          const uint32_t phi = tmem_p + sp * 2 * kWgPCols, plo = phi + kWgPCols;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_tf32_ts(acc, phi + kk * 8, d_qhi + 2 * kk, idesc, (i == 0 && kk == 0) ? 0u : 1u);
+            umma_tf32_ts(acc, plo + kk * 8, d_qhi + 2 * kk, idesc, 1);
+            umma_tf32_ts(acc, phi + kk * 8, d_qlo + 2 * kk, idesc, 1);
+          }
+          umma_commit(&p_empty[sp]);
+          sp ^= 1;
+          pp ^= (sp == 0);
+        }
+        umma_commit(&q_empty[rq.slot]);
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (warp < 10) {
+    // ===== P transform: TMEM lane = input channel; set s (warps 2-5 / 6-9) handles the blocks of parity s =====
+    const int quad = warp & 3, set = (warp - 2) >> 2;
+    const int ch = quad * 32 + lane;                          // channel within the p tile = TMEM lane
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t t_p = tmem_p + t_lane + set * 2 * kWgPCols;
+    constexpr int ch_stride = (kWgBlockPx / kW) * (kTaps == 9 ? kW + 8 : kW);   // floats per channel in the raw box
+    WgRing rp(kWgRawSlots);
+    int pp = 0, item = 0;   // phase of this set's stage; running (block, tap) work item: set s takes the items of parity s
+    constexpr bool kPad = kTaps == 9;
+    constexpr int kRows = kWgBlockPx / kW, kBoxW = kPad ? kW + 8 : kW;
+    constexpr int kRawVec = kRows * kBoxW / 4;
+    for (int i = 0; i < n_my; ++i, rp.next()) {
+      bool loaded = false;
+      float raw[kRawVec * 4];
+#pragma unroll
+      for (int t = 0; t < taps_here; ++t, ++item) {
+        if ((item & 1) != set) continue;
+        if (!loaded) {
+          // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
+          mbar_wait(&rawp_full[rp.slot], rp.phase);
+          const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + (ch * ch_stride) / 4;
+#pragma unroll
+          for (int j = 0; j < kRawVec; ++j) {
+            const float4 v = src[j];
+            raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
+          }
+          loaded = true;
+        }
+        mbar_wait(&p_empty[set], pp ^ 1);
+        pp ^= 1;
+        tc_fence_after();
+        // the 32 pixels shifted by this tap (x offset t - 1; box column = w + 4), ReLU, hi / lo split -> TMEM
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float h8[8], l8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int px = 8 * j + c;
+            float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];
+            if (a.relu_in) v = fmaxf(v, 0.f);
+            h8[c] = wg_trunc(v);
+            l8[c] = wg_round(v - h8[c]);
+          }
+          tmem_st_32x8(t_p + 8 * j, h8);
+          tmem_st_32x8(t_p + kWgPCols + 8 * j, l8);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[set]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box (or never needed it)
+    }
+    // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take alternate 32-column chunks =====
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int ci = p0 + ch;
+    const int n_here = min(128, a.Cout - q0);
+    const int n_chunks = (n_here + 31) / 32;
+    for (int t = 0; t < taps_here; ++t) {
+      const int tap = kTaps == 9 ? dy * 3 + t : 0;
+      float* dst = a.partial + (((int64_t)ks * a.taps + tap) * a.Cin + ci) * a.Cout + q0;
+      for (int c = set; c < n_chunks; c += 2) {
+        float v[32];
+        tmem_ld_32x32(tmem + t_lane + t * a.n_tile + c * 32, v);
+        if (ci < a.Cin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < n_here) dst[c * 32 + j] = v[j];
+        }
+      }
+    }
+  } else {
+    // ===== Q split: the TMA-loaded fp32 tile becomes its TF32 hi part in place, the lo part goes next to it =====
+    const int tid = threadIdx.x - 320;   // 0..127
+    WgRing rq(kWgQSlots);
+    const int n_vec = a.n_tile * (kWgBlockPx / 4);   // float4s of the tile
+    for (int i = 0; i < n_my; ++i, rq.next()) {
+      mbar_wait(&qraw_full[rq.slot], rq.phase);
+      float4* hi = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes);
+      float4* lo = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes + kWgQBytes);
+      for (int j = tid; j < n_vec; j += 128) {
+        const float4 v = hi[j];
+        float4 h, l;
+        h.x = wg_trunc(v.x); h.y = wg_trunc(v.y); h.z = wg_trunc(v.z); h.w = wg_trunc(v.w);
+        l.x = wg_round(v.x - h.x); l.y = wg_round(v.y - h.y); l.z = wg_round(v.z - h.z); l.w = wg_round(v.w - h.w);
+        hi[j] = h;
+        lo[j] = l;
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[rq.slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, a.tmem_cols);
+}
+
+// out[co][ci][tap] = sum over ks of partial[ks][tap][ci][co], added in index order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_ks, int taps, int Cin, int Cout) {
+  const int64_t n = (int64_t)taps * Cin * Cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes [tap][ci][co] (coalesced reads); the write is the permuted position
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int tap = (int)(i / ((int64_t)Cout * Cin));
+    float acc = 0.f;
+    for (int k = 0; k < n_ks; ++k) acc += partial[(int64_t)k * n + i];
+    out[((int64_t)co * Cin + ci) * taps + tap] = acc;
+  }
+}
+
+static int wgrad_splits(const mflow_conv_desc* d) {
+  const int n_dy = d->kernel == 3 ? 3 : 1;
+  const int tiles = (int)((d->c_in + 127) / 128) * (int)((d->c_out + 127) / 128);
+  const int64_t n_blocks = d->batch * d->height * d->width / kWgBlockPx;
+  int64_t ks = kNumSMs / (n_dy * tiles);
+  if (ks > n_blocks) ks = n_blocks;
+  if (ks < 1) ks = 1;
+  return (int)ks;
+}
+
+}  // namespace mflow
+
+using namespace mflow;
+
+extern "C" MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* d) {
+  if (!d) return 0;
+  const int64_t taps = d->kernel == 3 ? 9 : 1;
+  return (int64_t)wgrad_splits(d) * taps * d->c_in * d->c_out * (int64_t)sizeof(float);
+}
+
+extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, const float* x, const float* g_y, float* g_w,
+                                                   void* workspace, void* stream) {
+  MFLOW_REQUIRE(d && x && g_y && g_w && workspace, "null pointer");
+  MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
+  MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8, "width must be 8, 16 or 32");
+  MFLOW_REQUIRE(d->height == d->width, "square feature maps only");
+  MFLOW_REQUIRE(d->c_in >= 1 && d->c_out >= 1 && d->batch >= 1, "bad extents");
+  MFLOW_REQUIRE(d->kernel == 1 || d->c_out <= 112, "3x3 weight gradients support at most 112 output channels");
+  const int W = (int)d->width, H = (int)d->height, B = (int)d->batch;
+  WgradArgs a{};
+  a.partial = (float*)workspace;
+  a.B = B; a.Cin = (int)d->c_in; a.Cout = (int)d->c_out; a.H = H; a.W = W;
+  a.taps = d->kernel == 3 ? 9 : 1;
+  a.relu_in = d->relu_in;
+  a.rows = kWgBlockPx / W;
+  a.box_w = a.taps == 9 ? W + 8 : W;
+  a.raw_bytes = 128 * a.rows * a.box_w * 4;
+  a.blocks_per_img = H * W / kWgBlockPx;
+  a.n_blocks = B * a.blocks_per_img;
+  a.n_dy = a.taps == 9 ? 3 : 1;
+  const int q_tiles = (a.Cout + 127) / 128, p_tiles = (a.Cin + 127) / 128;
+  // one n_tile for the whole launch: a multiple of 16 covering the widest q tile
+  { const int widest = a.Cout < 128 ? a.Cout : 128; a.n_tile = (widest + 15) / 16 * 16; }
+  a.tmem_cols = 512;
+  MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + 4 * kWgPCols <= 512, "accumulators do not fit in tensor memory");
+  const int n_ks = wgrad_splits(d);
+
+  CUtensorMap mx, mg;
+  {  // activations, NCHW: box {box_w, rows, 128 channels, 1 image}; lands as [channel][row][w]
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.rows, 128u, 1u};
+    if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
+  }
+  {  // output gradient as [B][Cout][H*W]: box {32 pixels, n_tile channels, 1 image}, 128-byte swizzled K-major rows
+    cuuint64_t dims[3] = {(cuuint64_t)H * W, (cuuint64_t)a.Cout, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kWgBlockPx, (cuuint32_t)a.n_tile, 1u};
+    if (!encode(&mg, g_y, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
+  }
+  dim3 grid(n_ks, a.n_dy, q_tiles * p_tiles);
+  const size_t smem = (size_t)kWgQSlots * 2 * kWgQBytes + (size_t)kWgRawSlots * a.raw_bytes + 1024;
+  const cudaStream_t st = (cudaStream_t)stream;
+#define MFLOW_WGRAD_LAUNCH(WW, TT)                                                                                   \
+  do {                                                                                                               \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      cudaFuncSetAttribute(wgrad_tf32x3_kernel<WW, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);    \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    wgrad_tf32x3_kernel<WW, TT><<<grid, kWgThreads, smem, st>>>(mx, mg, a);                                          \
+  } while (0)
+  if (a.taps == 9) {
+    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 9); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 9); else MFLOW_WGRAD_LAUNCH(8, 9);
+  } else {
+    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 1); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 1); else MFLOW_WGRAD_LAUNCH(8, 1);
+  }
+#undef MFLOW_WGRAD_LAUNCH
+  const int64_t n_out = (int64_t)a.taps * a.Cin * a.Cout;
+  int rgrid = (int)((n_out + 255) / 256);
+  if (rgrid > 4 * kNumSMs) rgrid = 4 * kNumSMs;
+  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(a.partial, g_w, n_ks, a.taps, a.Cin, a.Cout);
+  return check_launch("wgrad_tf32x3_kernel");
+}

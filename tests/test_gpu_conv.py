@@ -100,3 +100,25 @@ def test_channel_sum_matches_fp64_sum(cuda_device, shape):
     assert got.shape == want.shape
     assert ((got.double() - want).abs() / scale).max().item() < 1e-6 if got.numel() else True
     assert torch.equal(got, ops.channel_sum(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(2, 100, 100, 32, 3, True), (3, 100, 100, 16, 3, True), (5, 100, 100, 8, 3, False), (2, 6, 100, 32, 1, False),
+                                  (2, 100, 192, 32, 1, True), (3, 100, 384, 16, 1, True), (2, 24, 100, 8, 1, False), (1, 8, 8, 32, 3, False),
+                                  (2, 130, 40, 16, 1, False), (7, 48, 100, 8, 1, True), (1, 1, 1, 8, 3, False)])
+def test_wgrad_tensor_core_matches_fp64_autograd(cuda_device, case):
+    """mflow_conv2d_wgrad_tf32x3 against the fp64 autograd weight gradient of F.conv2d (reference: nn/resnet.py conv layers)."""
+    from manifold_flow.b200 import ops
+
+    b, ci, co, hw, k, relu = case
+    torch.manual_seed(11)
+    x = torch.randn(b, ci, hw, hw, device=cuda_device)
+    g = torch.randn(b, co, hw, hw, device=cuda_device)
+    w = torch.zeros(co, ci, k, k, device=cuda_device, dtype=torch.float64, requires_grad=True)
+    xin = (F.relu(x) if relu else x).double()
+    F.conv2d(xin, w, padding=k // 2).backward(g.double())
+    got = ops.conv_wgrad_tc(g, x, k, relu)
+    assert got.shape == w.grad.shape
+    rel = ((got.double() - w.grad).norm() / w.grad.norm()).item()
+    assert rel < 2e-6, rel                                   # fp32 library wgrad sits at 1e-7 .. 2e-6 on these
+    assert torch.equal(got, ops.conv_wgrad_tc(g, x, k, relu))   # deterministic
