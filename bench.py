@@ -340,6 +340,7 @@ def run_b200(args):
         step_ms = 1e3 * secs / args.steps
         rqs = {k: v for k, v in summ.items() if k.startswith("rqs_")}
         conv = {k: v for k, v in summ.items() if k.startswith("conv")}
+        wgr = {k: v for k, v in summ.items() if k.startswith("wgrad")}
 
         def agg(group):
             return sum(v["bytes"] for v in group.values()), sum(v["ms"] for v in group.values())
@@ -361,6 +362,15 @@ def run_b200(args):
                     "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
                                        "useful_TFLOPs": v["bytes"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None} for k, v in conv.items()},
                     "secondary": spline}
+            if wgr:  # the weight-gradient kernel of the same convolutions (pixels-as-K GEMM, same 3xTF32 scheme)
+                wf, wms = agg(wgr)
+                wach = wf / (wms * 1e-3) / 1e12 if wms > 0 else None
+                roof["wgrad"] = {"bound": "tensor", "kernel": "wgrad_tf32x3_kernel (+ split-K reduce; all launches of a step)", "achieved": wach,
+                                 "peak": tc_peak, "unit": "TFLOP/s", "frac": wach / tc_peak if wach else None, "traffic": None,
+                                 "share_of_step": (wms / 2) / step_ms,
+                                 "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
+                                                    "useful_TFLOPs": v["bytes"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
+                                                for k, v in wgr.items()}}
         else:
             roof = spline
     cpu_base = None
@@ -384,7 +394,7 @@ def run_b200(args):
             "dtype": "f32" if config.conditioner_math == "fp32" else "f32 (tf32 conditioner GEMMs)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * b, "per_gpu_batch": b, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations + spline parameters, several GB) exceeds the 126 MB L2; 4 input batches rotate",
-                       "conditioner": ("image convolutions forward + data gradient: tcgen05 3xTF32 kernels of libmflow_b200; weight gradients, vector-conditioner GEMMs and the 3840-wide LU layers: cuDNN/cuBLAS fp32"
+                       "conditioner": ("image convolutions forward, data gradient and weight gradient: tcgen05 3xTF32 kernels of libmflow_b200 (4x4 feature maps' weight gradients: cuDNN); vector-conditioner GEMMs and the 3840-wide LU layers: cuBLAS fp32"
                                        if config.conv_tensor_cores else "cuBLAS/cuDNN fp32 library calls")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_secs / args.steps},

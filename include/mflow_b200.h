@@ -125,8 +125,8 @@ typedef struct {
 MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* desc, const float* x, const float* mat, const float* bias,
                         float* y, void* stream);
 /* Weight gradients of the above: g_mat[c,k] = sum_{o,i} g_y[o,c,i] x[o,k,i], g_bias[c] = sum g_y.
- * workspace: device scratch of mflow_chanmix_wgrad_workspace_bytes(desc) bytes; its first 16 bytes hold
- * an arrival counter that must be zero on first use (left zeroed by every launch). */
+ * Deterministic two-pass reduction.  workspace: device scratch of mflow_chanmix_wgrad_workspace_bytes(desc)
+ * bytes, no initialisation needed. */
 MFLOW_API int64_t mflow_chanmix_wgrad_workspace_bytes(const mflow_mix_desc* desc);
 MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* desc, const float* x, const float* g_y, float* g_mat,
                         float* g_bias, void* workspace, void* stream);

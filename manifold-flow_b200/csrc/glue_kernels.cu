@@ -76,11 +76,12 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
 }
 
 // g_mat[c,k] = sum_q g_y[c,q] x[k,q],  g_bias[c] = sum_q g_y[c,q]: each CTA accumulates a slab of
-// pixels into shared memory, writes its partial [C*C + C] block; the last-arriving CTA reduces the
-// partials in a fixed order (deterministic).
+// pixels into shared memory and writes its partial [C*C + C] block; a second kernel adds the partials in a
+// fixed order (deterministic).  (One CTA summing all partials at the end capped the grid at a few dozen CTAs
+// for 96 channels: 300 us for a 75 MFLOP problem.)
 __global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                                                                     float* __restrict__ g_mat, float* __restrict__ g_bias,
-                                                                    float* __restrict__ partial, unsigned int* counter,
+                                                                    float* __restrict__ partial,
                                                                     int64_t n_pix, int C, int64_t I, int64_t x_so, int64_t x_sc,
                                                                     int64_t x_si, int64_t y_so, int64_t y_sc, int64_t y_si) {
   extern __shared__ float smem[];
@@ -88,7 +89,6 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float*
   float* s_acc = smem;                  // [C*C + C]
   float* s_x = s_acc + C * C + C;       // [C][33]
   float* s_g = s_x + C * pitch;         // [C][33]
-  __shared__ int s_last;
   const int n_out = C * C + C;
   for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) s_acc[idx] = 0.f;
   const bool chan_fast = (x_sc == 1);
@@ -126,19 +126,17 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float*
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) partial[(int64_t)blockIdx.x * n_out + idx] = s_acc[idx];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // final reduction over the CTA partials in a fixed order; consecutive threads read consecutive outputs
-  for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) {
-    float acc = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (int64_t)b * n_out + idx);
-    if (idx < C * C) g_mat[idx] = acc; else if (g_bias) g_bias[idx - C * C] = acc;
-  }
-  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// second pass: add the CTA partials in index order (deterministic); consecutive threads read consecutive outputs
+__global__ void chanmix_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ g_mat, float* __restrict__ g_bias,
+                                            int n_parts, int C) {
+  const int n_out = C * C + C;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out) return;
+  float acc = 0.f;
+  for (int b = 0; b < n_parts; ++b) acc += partial[(int64_t)b * n_out + idx];
+  if (idx < C * C) g_mat[idx] = acc; else if (g_bias) g_bias[idx - C * C] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,11 +332,10 @@ static unsigned grid_for(int64_t total, int threads) {
 static size_t mix_smem(int C) { return (size_t)(C * C + C * (kMixPix + 1) + C) * sizeof(float); }
 static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
 static int wgrad_grid(int64_t n_pix, int64_t n_chan) {
-  // as many CTAs as pixel tiles, up to 8 per SM, but the last-arriving CTA sums all partial blocks alone:
-  // keep (CTAs x outputs) below 256K values (1 MB) so that this tail stays at a few microseconds
+  // as many CTAs as pixel tiles, up to 8 per SM; the partial blocks stay below 8 MB
   int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
   int64_t cap = (int64_t)kNumSMs * 8;
-  const int64_t budget = (256 * 1024) / (n_chan * n_chan + n_chan);
+  const int64_t budget = (2 * 1024 * 1024) / (n_chan * n_chan + n_chan);
   if (cap > budget) cap = budget;
   if (cap < 8) cap = 8;
   return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
@@ -377,15 +374,12 @@ extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const floa
   const int C = (int)d->n_chan;
   const int grid = wgrad_grid(n_pix, C);
   const int64_t n_out = (int64_t)C * C + C;
-  // arrival counter in the first 16 bytes (zero between launches), partial blocks after it
-  unsigned int* counter = (unsigned int*)workspace;
   float* partial = (float*)((char*)workspace + 16);
-  (void)n_out;
   const size_t smem = wgrad_smem(C);
   if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  chanmix_wgrad_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, g_y, g_mat, g_bias, partial, counter,
-                                                                            n_pix, C, d->n_inner, d->x_so, d->x_sc, d->x_si,
-                                                                            d->y_so, d->y_sc, d->y_si);
+  chanmix_wgrad_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, g_y, g_mat, g_bias, partial, n_pix, C, d->n_inner,
+                                                                            d->x_so, d->x_sc, d->x_si, d->y_so, d->y_sc, d->y_si);
+  chanmix_wgrad_reduce_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, g_mat, g_bias, grid, C);
   return check_launch("chanmix_wgrad_kernel");
 }
 
