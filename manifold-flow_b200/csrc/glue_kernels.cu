@@ -21,56 +21,78 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
                                                               const float* __restrict__ bias, float* __restrict__ y,
                                                               int64_t n_pix, int C, int64_t I, int64_t x_so, int64_t x_sc,
                                                               int64_t x_si, int64_t y_so, int64_t y_sc, int64_t y_si) {
-  extern __shared__ float smem[];
-  float* s_mat = smem;                 // [C][C]
-  float* s_x = smem + C * C;           // [C][33]
-  float* s_b = s_x + C * (kMixPix + 1);  // [C]
-  for (int idx = threadIdx.x; idx < C * C; idx += kMixThreads) s_mat[idx] = mat[idx];
-  for (int idx = threadIdx.x; idx < C; idx += kMixThreads) s_b[idx] = bias ? bias[idx] : 0.f;
-  const int64_t q0 = (int64_t)blockIdx.x * kMixPix;
-  const int n_here = (int)min((int64_t)kMixPix, n_pix - q0);
+  // The CTA keeps the matrix (transposed, [k][c] with c padded to a multiple of 4) in shared memory and walks
+  // pixel tiles grid-stride, so the matrix is fetched once per CTA, not once per 32 pixels.  A thread produces
+  // four output channels of one pixel at a time: per k one activation load and one 16-byte matrix load
+  // (a broadcast) feed four FMAs.
+  extern __shared__ __align__(16) float smem[];
+  const int Cp = (C + 3) & ~3;
+  float* s_matT = smem;                 // [C][Cp]
+  float* s_x = smem + C * Cp;           // [C][33]
+  float* s_b = s_x + C * (kMixPix + 1);  // [Cp]
+  for (int idx = threadIdx.x; idx < C * Cp; idx += kMixThreads) {
+    const int k = idx / Cp, c = idx - k * Cp;
+    s_matT[idx] = c < C ? mat[c * C + k] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < Cp; idx += kMixThreads) s_b[idx] = (bias && idx < C) ? bias[idx] : 0.f;
   const bool chan_fast = (x_sc == 1);  // rows layout: channels contiguous -> walk channels fastest
-  for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixThreads) {
-    int k, pq;
-    if (chan_fast) { pq = idx / C; k = idx - pq * C; } else { k = idx / kMixPix; pq = idx - k * kMixPix; }
-    float v = 0.f;
-    if (pq < n_here) {
-      const int64_t q = q0 + pq, o = q / I, i = q - o * I;
-      v = x[o * x_so + k * x_sc + i * x_si];
-    }
-    s_x[k * (kMixPix + 1) + pq] = v;
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (y_sc == 1) {
-    // rows layout: transpose through shared memory so that stores are contiguous
-    __shared__ float s_y[kMixPix][33];
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      for (int cc = warp; cc < 32 && c0 + cc < C; cc += 4) {
-        const int c = c0 + cc;
-        float acc = s_b[c];
-        for (int k = 0; k < C; ++k) acc = fmaf(s_mat[c * C + k], s_x[k * (kMixPix + 1) + lane], acc);
-        s_y[lane][cc] = acc;
+  const int64_t n_tiles = (n_pix + kMixPix - 1) / kMixPix;
+  __shared__ float s_y[kMixPix][33];
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t q0 = tile * kMixPix;
+    const int n_here = (int)min((int64_t)kMixPix, n_pix - q0);
+    __syncthreads();   // the previous tile's readers are done with s_x (and the matrix is in place)
+    for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixThreads) {
+      int k, pq;
+      if (chan_fast) { pq = idx / C; k = idx - pq * C; } else { k = idx / kMixPix; pq = idx - k * kMixPix; }
+      float v = 0.f;
+      if (pq < n_here) {
+        const int64_t q = q0 + pq, o = q / I, i = q - o * I;
+        v = x[o * x_so + k * x_sc + i * x_si];
       }
-      __syncthreads();
-      const int nc = min(32, C - c0);
-      for (int idx = threadIdx.x; idx < kMixPix * nc; idx += kMixThreads) {
-        const int pq = idx / nc, cc = idx - pq * nc;
-        if (pq < n_here) {
-          const int64_t q = q0 + pq, o = q / I, i = q - o * I;
-          y[o * y_so + (c0 + cc) * y_sc + i * y_si] = s_y[pq][cc];
-        }
-      }
-      __syncthreads();
+      s_x[k * (kMixPix + 1) + pq] = v;
     }
-    return;
-  }
-  if (lane < n_here) {
-    const int64_t q = q0 + lane, o = q / I, i = q - o * I;
-    for (int c = warp; c < C; c += 4) {
-      float acc = s_b[c];
-      for (int k = 0; k < C; ++k) acc = fmaf(s_mat[c * C + k], s_x[k * (kMixPix + 1) + lane], acc);
-      y[o * y_so + c * y_sc + i * y_si] = acc;
+    __syncthreads();
+    if (y_sc == 1) {
+      // rows layout: transpose through shared memory so that stores are contiguous
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int cc = warp * 4; cc < 32 && c0 + cc < C; cc += 16) {
+          const int c = c0 + cc;
+          float a0 = s_b[c], a1 = s_b[c + 1], a2 = s_b[c + 2], a3 = s_b[c + 3];
+          for (int k = 0; k < C; ++k) {
+            const float xv = s_x[k * (kMixPix + 1) + lane];
+            const float4 m = *reinterpret_cast<const float4*>(s_matT + k * Cp + c);
+            a0 = fmaf(m.x, xv, a0); a1 = fmaf(m.y, xv, a1); a2 = fmaf(m.z, xv, a2); a3 = fmaf(m.w, xv, a3);
+          }
+          s_y[lane][cc] = a0; s_y[lane][cc + 1] = a1; s_y[lane][cc + 2] = a2; s_y[lane][cc + 3] = a3;
+        }
+        __syncthreads();
+        const int nc = min(32, C - c0);
+        for (int idx = threadIdx.x; idx < kMixPix * nc; idx += kMixThreads) {
+          const int pq = idx / nc, cc = idx - pq * nc;
+          if (pq < n_here) {
+            const int64_t q = q0 + pq, o = q / I, i = q - o * I;
+            y[o * y_so + (c0 + cc) * y_sc + i * y_si] = s_y[pq][cc];
+          }
+        }
+        __syncthreads();
+      }
+    } else if (lane < n_here) {
+      const int64_t q = q0 + lane, o = q / I, i = q - o * I;
+      float* yq = y + o * y_so + i * y_si;
+      for (int c = warp * 4; c < C; c += 16) {
+        float a0 = s_b[c], a1 = s_b[c + 1], a2 = s_b[c + 2], a3 = s_b[c + 3];
+        for (int k = 0; k < C; ++k) {
+          const float xv = s_x[k * (kMixPix + 1) + lane];
+          const float4 m = *reinterpret_cast<const float4*>(s_matT + k * Cp + c);
+          a0 = fmaf(m.x, xv, a0); a1 = fmaf(m.y, xv, a1); a2 = fmaf(m.z, xv, a2); a3 = fmaf(m.w, xv, a3);
+        }
+        yq[c * y_sc] = a0;
+        if (c + 1 < C) yq[(c + 1) * y_sc] = a1;
+        if (c + 2 < C) yq[(c + 2) * y_sc] = a2;
+        if (c + 3 < C) yq[(c + 3) * y_sc] = a3;
+      }
     }
   }
 }
@@ -128,15 +150,25 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_wgrad_kernel(const float*
   for (int idx = threadIdx.x; idx < n_out; idx += kMixThreads) partial[(int64_t)blockIdx.x * n_out + idx] = s_acc[idx];
 }
 
-// second pass: add the CTA partials in index order (deterministic); consecutive threads read consecutive outputs
-__global__ void chanmix_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ g_mat, float* __restrict__ g_bias,
-                                            int n_parts, int C) {
+// second pass: add the CTA partials (deterministic: fixed assignment, fixed tree).  A block owns 32 consecutive
+// outputs; its 32 rows of threads sweep the partial blocks (coalesced 128-byte reads), then the rows are added
+// in order through shared memory.
+__global__ void __launch_bounds__(1024) chanmix_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ g_mat,
+                                                                    float* __restrict__ g_bias, int n_parts, int C) {
+  __shared__ float s_red[32][33];
   const int n_out = C * C + C;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_out) return;
+  const int idx = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int b = 0; b < n_parts; ++b) acc += partial[(int64_t)b * n_out + idx];
-  if (idx < C * C) g_mat[idx] = acc; else if (g_bias) g_bias[idx - C * C] = acc;
+  if (idx < n_out)
+    for (int b = threadIdx.y; b < n_parts; b += 32) acc += partial[(int64_t)b * n_out + idx];
+  s_red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < n_out) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += s_red[r][threadIdx.x];
+    if (idx < C * C) g_mat[idx] = t; else if (g_bias) g_bias[idx - C * C] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,7 +361,7 @@ static unsigned grid_for(int64_t total, int threads) {
   return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-static size_t mix_smem(int C) { return (size_t)(C * C + C * (kMixPix + 1) + C) * sizeof(float); }
+static size_t mix_smem(int C) { const int Cp = (C + 3) & ~3; return (size_t)(C * Cp + C * (kMixPix + 1) + Cp) * sizeof(float); }
 static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
 static int wgrad_grid(int64_t n_pix, int64_t n_chan) {
   // as many CTAs as pixel tiles, up to 8 per SM; the partial blocks stay below 8 MB
@@ -354,7 +386,8 @@ extern "C" MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* d, const floa
   const int C = (int)d->n_chan;
   const size_t smem = mix_smem(C);
   if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const unsigned grid = (unsigned)((n_pix + kMixPix - 1) / kMixPix);
+  int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
+  const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);   // grid-stride over the pixel tiles
   chanmix_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, mat, bias, y, n_pix, C, d->n_inner, d->x_so, d->x_sc,
                                                                       d->x_si, d->y_so, d->y_sc, d->y_si);
   return check_launch("chanmix_kernel");
@@ -379,7 +412,7 @@ extern "C" MFLOW_API int mflow_chanmix_wgrad(const mflow_mix_desc* d, const floa
   if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   chanmix_wgrad_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, g_y, g_mat, g_bias, partial, n_pix, C, d->n_inner,
                                                                             d->x_so, d->x_sc, d->x_si, d->y_so, d->y_sc, d->y_si);
-  chanmix_wgrad_reduce_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, g_mat, g_bias, grid, C);
+  chanmix_wgrad_reduce_kernel<<<(unsigned)((n_out + 31) / 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(partial, g_mat, g_bias, grid, C);
   return check_launch("chanmix_wgrad_kernel");
 }
 
