@@ -357,7 +357,8 @@ def run_b200(args):
             ach = cf / (cms * 1e-3) / 1e12 if cms > 0 else None
             roof = {"bound": "tensor", "kernel": "conv_tf32x3_kernel (tcgen05 + TMA implicit-GEMM conv, 3xTF32 = 3 tensor passes per useful FLOP; all launches of a step)",
                     "achieved": ach, "peak": tc_peak, "peak_source": tc_src, "unit": "TFLOP/s", "frac": ach / tc_peak if ach else None,
-                    "traffic": None, "share_of_step": (cms / 2) / step_ms,
+                    "traffic": 167.44e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one level-0 3x3 launch (B=256, 100->100, 32x32) from the ncu --set full capture in profiles/r1_conv_tf32x3_ncu_full.md; algorithmic 209.7e6 (part of the output is still in L2 when the kernel ends)",
+                    "share_of_step": (cms / 2) / step_ms,
                     "note": "achieved counts useful fp32-equivalent FLOPs; the tensor pipe executes 3x that in TF32 (nominal TF32 peak is half the bf16 peak)",
                     "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
                                        "useful_TFLOPs": v["bytes"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None} for k, v in conv.items()},
