@@ -219,9 +219,13 @@ def run_b200(args):
     with torch.no_grad():  # data-dependent ActNorm init (rank 0's statistics are broadcast)
         model(dev_pool[0][0], mode="projection", context=dev_pool[0][1])
     ddp.broadcast_parameters(model, src=0)
-    reducer = ddp.GradientAllReducer(model.parameters(), bucket_mb=64.0) if world > 1 else None
+    use_graph = not args.no_graph
+    # Multi-GPU: with a captured step the gradients are all-reduced after the replay (flat buckets, NCCL on the same
+    # stream); the eager path overlaps the bucket all-reduces with backward through post-accumulate hooks.
+    reducer = ddp.GradientAllReducer(model.parameters(), bucket_mb=64.0, overlap=not use_graph) if world > 1 else None
 
-    def step(x, c):
+    def local_step(x, c):
+        """forward + backward on this rank's shard (the part that is captured into a CUDA graph)"""
         if reducer is not None:
             reducer.zero_grad()
         else:
@@ -229,14 +233,18 @@ def run_b200(args):
         log_prob = model(x, mode="mf-fixed-manifold", context=c)[1]
         loss = -log_prob.mean()
         loss.backward()
+        return loss
+
+    def step(x, c):
+        loss = local_step(x, c)
         if reducer is not None:
             reducer.finish()
         return loss
 
-    # ---- CUDA graph of the whole step (forward + backward), single GPU: ~4900 launches become one replay ----
+    # ---- CUDA graph of the local step (forward + backward): ~4800 launches become one replay ----
     graph = None
     static_x = static_c = static_loss = None
-    if world == 1 and not args.no_graph:
+    if use_graph:
         try:
             static_x, static_c = dev_pool[0][0].clone(), dev_pool[0][1].clone()
             side = torch.cuda.Stream()
@@ -246,25 +254,36 @@ def run_b200(args):
                     step(static_x, static_c)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            model.zero_grad(set_to_none=True)
+            if reducer is None:
+                model.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step(static_x, static_c)
+                static_loss = local_step(static_x, static_c)
             graph.replay()
+            if reducer is not None:
+                reducer.finish()
             torch.cuda.synchronize()
         except Exception as exc:  # capture is an optimisation: report and fall back to eager launches
             print(f"[bench] CUDA graph capture failed, running eagerly: {type(exc).__name__}: {str(exc)[:200]}", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()
+        if world > 1:  # all ranks must take the same path (the eager one needs the overlap hooks' bookkeeping off)
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if int(ok) == 0:
+                graph = None
 
     def run_step(x, c, on_device):
         """One step on batch (x, c).  With a graph the batch is copied into the graph's static inputs
-        (device->device for resident data, host->device for the end-to-end arm) and the graph replayed."""
+        (device->device for resident data, host->device for the end-to-end arm), the graph replayed and,
+        on several GPUs, the gradient buckets all-reduced."""
         if graph is None:
             return step(x, c)
         static_x.copy_(x, non_blocking=True)
         static_c.copy_(c, non_blocking=True)
         graph.replay()
+        if reducer is not None:
+            reducer.finish()
         return static_loss
 
     def barrier():
