@@ -63,6 +63,8 @@ struct ConvArgs {
   int raw_tx;             // true bytes of one raw box (all 32 channels, all images of the tile)
   int n_tile;             // MMA N extent: 112 when Cout <= 112 (13% less weight traffic and MMA time), else 128
   int n_raw, n_b;         // ring depths: raw boxes, weight tiles
+  int w_tile_bytes;       // one weight operand tile (hi or lo): w_rows x 128 bytes, w_rows = C_out of the tile rounded up to 8
+  int ring_bytes;         // weight ring (also the epilogue's staging area): max(n_b x 2 x w_tile_bytes, chunks x 16 KB)
   int aux_mode;           // 0 none, 1 residual add, 2 ReLU mask (gate)
   int aux_chunks;         // 32-channel boxes of the aux tile to fetch (0 when aux_mode == 0)
   int debug;              // profiling aid (MFLOW_CONV_DEBUG): bit0 skip MMAs, bit1 skip transform math, bit2 skip stores
@@ -72,6 +74,11 @@ __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__
 // round to nearest TF32 (ties away): the tensor core truncates its fp32 inputs, so the low part of the
 // split is pre-rounded to keep the truncation from biasing the sum
 __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+// Debugging aid (MFLOW_CONV_DEBUG bit 3): CTA (0,0) stamps clock64() per pipeline step:
+// [0][s] transform start (stage free), [1][s] transform done, [2][s] MMA issue (operands ready), [3][s] raw box ready (per kb),
+// [4][0] kernel start, [4][1] accumulator complete, [4][2] epilogue done
+__device__ long long g_conv_trace[5][64];
 
 // ring cursor without divisions: slot index + phase parity
 struct Ring {
@@ -84,15 +91,27 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_aux,
                    const __grid_constant__ CUtensorMap map_y, const ConvArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through uintptr_t makes the
-  // compiler forget the address space and emit generic loads for the activation gather)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_b = smem;                              // n_b x {B_hi 16 KB, B_lo 16 KB}
-  uint8_t* s_raw = s_b + a.n_b * 2 * kStageBytes;   // n_raw x raw box
-  __shared__ __align__(8) uint64_t raw_full[kMaxRaw], raw_empty[kMaxRaw], b_full[kMaxStagesB], b_empty[kMaxStagesB],
-      a_full[kStagesA], a_empty[kStagesA], acc_full, aux_full;
-  __shared__ uint32_t s_tmem;
+  // The kernel has NO static shared memory, so the dynamic array starts at the CTA's (1 KB aligned) base and the
+  // 128-byte-swizzled weight tiles need no alignment slack: two raw boxes + two weight stages + the barriers
+  // are 114.9 KB, which still lets two CTAs share an SM.  (Pointers are derived from the __shared__ array by
+  // pointer arithmetic: a cast through uintptr_t makes the compiler forget the address space and emit generic
+  // loads for the activation gather.)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_b = smem;                               // n_b x {B_hi, B_lo} weight tiles
+  uint8_t* s_raw = s_b + a.ring_bytes;               // n_raw x raw box
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + a.n_raw * a.raw_bytes);
+  uint64_t* raw_full = bars;                         // [kMaxRaw]
+  uint64_t* raw_empty = raw_full + kMaxRaw;          // [kMaxRaw]
+  uint64_t* b_full = raw_empty + kMaxRaw;            // [kMaxStagesB]
+  uint64_t* b_empty = b_full + kMaxStagesB;          // [kMaxStagesB]
+  uint64_t* a_full = b_empty + kMaxStagesB;          // [kStagesA]
+  uint64_t* a_empty = a_full + kStagesA;             // [kStagesA]
+  uint64_t* acc_full_p = a_empty + kStagesA;
+  uint64_t* aux_full_p = acc_full_p + 1;
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(aux_full_p + 1);
+#define acc_full (*acc_full_p)
+#define aux_full (*aux_full_p)
+#define s_tmem (*s_tmem_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -118,6 +137,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  const bool trace = (a.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0;
+  if (trace && threadIdx.x == 0) g_conv_trace[4][0] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -129,9 +150,9 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
-          mbar_expect_tx(&b_full[sb.slot], 2 * a.n_tile * kBlockK * 4);
-          tma_load_3d(s_b + sb.slot * 2 * kStageBytes, &map_whi, &b_full[sb.slot], kb * kBlockK, n0, tap);
-          tma_load_3d(s_b + sb.slot * 2 * kStageBytes + kStageBytes, &map_wlo, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          mbar_expect_tx(&b_full[sb.slot], 2 * a.w_tile_bytes);
+          tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes, &map_whi, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes + a.w_tile_bytes, &map_wlo, &b_full[sb.slot], kb * kBlockK, n0, tap);
         }
       }
       // Epilogue operand (residual or ReLU mask, shaped like the output): once the last MMA has drained the
@@ -159,10 +180,11 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           mbar_wait(&a_full[sa.slot], sa.phase);
           mbar_wait(&b_full[sb.slot], sb.phase);
           tc_fence_after();
+          if (trace && kb * a.taps + tap < 64) g_conv_trace[2][kb * a.taps + tap] = clock64();
           const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kBlockK, alo = ahi + kBlockK;
-          const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * kStageBytes);
+          const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * a.w_tile_bytes);
           // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes (2 descriptor units) further along each row
-          const uint64_t d_bhi = smem_desc(bhi, 16, 1024, 2), d_blo = smem_desc(bhi + kStageBytes, 16, 1024, 2);
+          const uint64_t d_bhi = smem_desc(bhi, 16, 1024, 2), d_blo = smem_desc(bhi + a.w_tile_bytes, 16, 1024, 2);
           if (ksteps == 4) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -200,6 +222,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
       const int nch = (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
       mbar_wait(&raw_full[rb.slot], rb.phase);
+      if (trace && warp == 2 && lane == 0 && kb < 64) g_conv_trace[3][kb] = clock64();
       const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
         if (step != half) continue;
@@ -207,6 +230,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(&a_empty[half], pa ^ 1);
         pa ^= 1;
         tc_fence_after();
+        const int step_id = kb * a.taps + tap;
+        if (trace && (warp == 2 || warp == 6) && lane == 0 && step_id < 64) g_conv_trace[0][step_id] = clock64();
         // gather the pixel's channels of the tap, optional ReLU, TF32 hi / lo split, and store both parts
         // into the pixel's TMEM lane (A_hi columns [0,32), A_lo columns [32,64) of the stage)
         if (!(a.debug & 2)) {
@@ -231,6 +256,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[half]);
+        if (trace && (warp == 2 || warp == 6) && lane == 0 && step_id < 64) g_conv_trace[1][step_id] = clock64();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rb.slot]);   // this warp's reads of the box are program-ordered before
@@ -238,6 +264,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    if (trace && warp == 2 && lane == 0) g_conv_trace[4][1] = clock64();
     // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
     const int tile_px = a.rows_per_tile * a.W;
     float* stage = reinterpret_cast<float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
@@ -271,13 +298,23 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 0) g_conv_trace[4][2] = clock64();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
+#undef acc_full
+#undef aux_full
+#undef s_tmem
+constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kStagesA + 2) * 8 + 16;
 
 // ---- host side --------------------------------------------------------------------------------
 }  // namespace mflow
 
 using namespace mflow;
+
+// debugging aid, not part of the ABI: copy out the step trace written under MFLOW_CONV_DEBUG=8
+extern "C" MFLOW_API int mflow_debug_conv_trace(long long* out320) {
+  return cudaMemcpyFromSymbol(out320, g_conv_trace, sizeof(long long) * 5 * 64) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+}
 
 extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const float* x, const float* w_hi, const float* w_lo,
                                              const float* bias, const float* residual, const float* gate, float* y,
@@ -307,22 +344,44 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   a.raw_bytes = (a.raw_tx + 1023) / 1024 * 1024;
   a.n_tile = a.Cout <= 112 ? 112 : 128;
   { const char* dbg = getenv("MFLOW_CONV_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
-  // Ring depths: prefer a footprint that lets two CTAs share an SM (each at most ~110 KB), which hides one
-  // CTA's prologue / epilogue behind the other's main loop; fall back to deeper rings, one CTA per SM.
-  const int two_cta_budget = 110 * 1024, one_cta_budget = 225 * 1024;
-  const int steps = a.k_blocks * a.taps;
-  a.n_b = steps < 2 ? 1 : 2; a.n_raw = 1;
-  if (a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes > two_cta_budget) { a.n_b = 4; a.n_raw = 1; }
-  MFLOW_REQUIRE(a.n_b * 2 * kStageBytes + a.n_raw * a.raw_bytes <= one_cta_budget, "tile does not fit in shared memory");
-
+  // Weight tiles: only the rows that hold output channels travel (rounded up to the 8-row swizzle atom); the
+  // MMA's N extent may reach past them into whatever follows in shared memory - those accumulator columns
+  // belong to channels >= C_out and are never stored.
+  const int n_here_max = a.Cout < kTileN ? a.Cout : kTileN;
+  const int w_rows = (n_here_max + 7) / 8 * 8;
+  a.w_tile_bytes = w_rows * kBlockK * 4;
   a.aux_mode = residual ? 1 : (gate ? 2 : 0);
-  {
-    const int n_here = a.Cout < kTileN ? a.Cout : kTileN;
-    a.aux_chunks = a.aux_mode ? (n_here + 31) / 32 : 0;
-    const int out_chunks = (n_here + 31) / 32;  // the output tile is staged in the weight ring as well
-    if (out_chunks * kStageBytes > a.n_b * 2 * kStageBytes) a.n_b = 2;
-    MFLOW_REQUIRE(a.aux_chunks * kStageBytes <= a.n_b * 2 * kStageBytes, "aux tile does not fit in the weight ring");
+  const int out_chunks = (n_here_max + 31) / 32;   // the output (and aux) tile is staged in the weight ring, 16 KB per 32 channels
+  a.aux_chunks = a.aux_mode ? out_chunks : 0;
+  // Shared memory: weight ring + raw-box ring + barriers.  Prefer a footprint that lets two CTAs share an SM
+  // (dynamic + 1 KB reserved <= 114 KB each: one CTA's prologue / epilogue hides behind the other's main loop),
+  // and within it a second raw box before a third weight stage: a single raw box costs ~5000 idle cycles at every
+  // 32-channel block boundary (measured with the step trace), the weight tiles arrive in ~700.  Else one CTA per SM
+  // with both rings deep.  The epilogue stages its output / aux tile over the drained rings.
+  const int two_cta_budget = 114 * 1024 - 512, one_cta_budget = 226 * 1024;
+  const int steps = a.k_blocks * a.taps;
+  // bytes of the two rings; never less than the epilogue's staging tile, which is laid over them
+  auto rings = [&](int n_raw, int n_b) {
+    const int r = n_b * 2 * a.w_tile_bytes + n_raw * a.raw_bytes, o = out_chunks * kStageBytes;
+    return r > o ? r : o;
+  };
+  auto total = [&](int n_raw, int n_b) { return rings(n_raw, n_b) + kConvBarrierBytes; };
+  const int prefs[][2] = {{2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
+  a.n_b = 0;
+  for (auto& pr : prefs)
+    if (total(pr[0], pr[1]) <= two_cta_budget) { a.n_raw = pr[0]; a.n_b = pr[1]; break; }
+  if (a.n_b == 0) {
+    a.n_raw = 2; a.n_b = kMaxStagesB;
+    while (a.n_b > 2 && total(a.n_raw, a.n_b) > one_cta_budget) --a.n_b;
+    if (total(a.n_raw, a.n_b) > one_cta_budget) a.n_raw = 1;
   }
+  if (a.n_b > steps) a.n_b = steps;
+  if (a.n_raw > a.k_blocks) a.n_raw = a.k_blocks;
+  { const char* e = getenv("MFLOW_CONV_NB"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxStagesB) a.n_b = atoi(e); }
+  { const char* e = getenv("MFLOW_CONV_NRAW"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxRaw) a.n_raw = atoi(e); }
+  a.ring_bytes = rings(a.n_raw, a.n_b) - a.n_raw * a.raw_bytes;   // weight ring, padded when the staging tile needs more
+  MFLOW_REQUIRE(total(a.n_raw, a.n_b) <= one_cta_budget, "tile does not fit in shared memory");
+
   CUtensorMap mx, mhi, mlo, maux, my;
   {  // output, NCHW: box {W, rows, 32 channels, images}
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
@@ -346,13 +405,13 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   {  // weights: [taps][n_pad][k_pad], K-major 128B-swizzled tiles of n_tile x 32
     cuuint64_t dims[3] = {(cuuint64_t)d->k_pad, (cuuint64_t)d->n_pad, (cuuint64_t)a.taps};
     cuuint64_t str[2] = {(cuuint64_t)d->k_pad * 4, (cuuint64_t)d->k_pad * d->n_pad * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)a.n_tile, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)w_rows, 1};
     if (!encode(&mhi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
     if (!encode(&mlo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
   }
   const int n_tiles = a.imgs_per_tile > 1 ? (B + a.imgs_per_tile - 1) / a.imgs_per_tile : B * (H / a.rows_per_tile);
   dim3 grid(n_tiles, (a.Cout + kTileN - 1) / kTileN);
-  const size_t smem = (size_t)a.n_b * 2 * kStageBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
+  const size_t smem = (size_t)total(a.n_raw, a.n_b);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
