@@ -13,6 +13,7 @@ from torch import nn
 from torch.nn import functional as F
 from torch.nn import init
 
+from ..b200 import ops
 from ..b200.cabi import require_cuda
 from ..utils import various
 from .base import Transform
@@ -125,8 +126,12 @@ class LULinear(Linear):
             outputs = F.linear(F.linear(inputs, upper), lower, self.bias)
             return outputs, self.logabsdet()
         outputs = (inputs - self.bias).t()  # lu.py:75-95
-        outputs = torch.linalg.solve_triangular(lower, outputs, upper=False, unitriangular=True)
-        outputs = torch.linalg.solve_triangular(upper, outputs, upper=True)
+        if self.features >= 1024:   # wide layers: blocked substitution on GEMMs (b200/ops.py)
+            outputs = ops.tri_solve(lower, outputs, upper=False, unit=True)
+            outputs = ops.tri_solve(upper, outputs, upper=True)
+        else:
+            outputs = torch.linalg.solve_triangular(lower, outputs, upper=False, unitriangular=True)
+            outputs = torch.linalg.solve_triangular(upper, outputs, upper=True)
         return outputs.t(), -self.logabsdet()
 
     # reference spelling of the two directions
