@@ -64,6 +64,7 @@ struct ConvArgs {
   int n_tile;             // MMA N extent: 112 when Cout <= 112 (13% less weight traffic and MMA time), else 128
   int n_raw, n_b;         // ring depths: raw boxes, weight tiles
   int w_tile_bytes;       // one weight operand tile (hi or lo): w_rows x 128 bytes, w_rows = C_out of the tile rounded up to 8
+  int tail_k8;            // the last channel block has <= 8 channels: its weight tiles travel as 32-byte rows
   int ring_bytes;         // weight ring (also the epilogue's staging area): max(n_b x 2 x w_tile_bytes, chunks x 16 KB)
   int aux_mode;           // 0 none, 1 residual add, 2 ReLU mask (gate)
   int aux_chunks;         // 32-channel boxes of the aux tile to fetch (0 when aux_mode == 0)
@@ -89,7 +90,8 @@ struct Ring {
 
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_aux,
+                   const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_whi8,
+                   const __grid_constant__ CUtensorMap map_wlo8, const __grid_constant__ CUtensorMap map_aux,
                    const __grid_constant__ CUtensorMap map_y, const ConvArgs a) {
   // The kernel has NO static shared memory, so the dynamic array starts at the CTA's (1 KB aligned) base and the
   // 128-byte-swizzled weight tiles need no alignment slack: two raw boxes + two weight stages + the barriers
@@ -150,9 +152,17 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
-          mbar_expect_tx(&b_full[sb.slot], 2 * a.w_tile_bytes);
-          tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes, &map_whi, &b_full[sb.slot], kb * kBlockK, n0, tap);
-          tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes + a.w_tile_bytes, &map_wlo, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          if (a.tail_k8 && kb == a.k_blocks - 1) {
+            // last channel block with at most 8 channels: 32-byte rows (32B swizzle) instead of 128-byte ones -
+            // the kernel is bound by the L2 -> shared weight traffic, and this block would be 3/4 zero padding
+            mbar_expect_tx(&b_full[sb.slot], a.w_tile_bytes / 2);
+            tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes, &map_whi8, &b_full[sb.slot], kb * kBlockK, n0, tap);
+            tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes + a.w_tile_bytes, &map_wlo8, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          } else {
+            mbar_expect_tx(&b_full[sb.slot], 2 * a.w_tile_bytes);
+            tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes, &map_whi, &b_full[sb.slot], kb * kBlockK, n0, tap);
+            tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes + a.w_tile_bytes, &map_wlo, &b_full[sb.slot], kb * kBlockK, n0, tap);
+          }
         }
       }
       // Epilogue operand (residual or ReLU mask, shaped like the output): once the last MMA has drained the
@@ -184,7 +194,9 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kBlockK, alo = ahi + kBlockK;
           const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * a.w_tile_bytes);
           // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes (2 descriptor units) further along each row
-          const uint64_t d_bhi = smem_desc(bhi, 16, 1024, 2), d_blo = smem_desc(bhi + a.w_tile_bytes, 16, 1024, 2);
+          const bool tail8 = a.tail_k8 && kb == a.k_blocks - 1;   // 32-byte rows, 32B swizzle: 8-row groups 256 bytes apart
+          const uint64_t d_bhi = tail8 ? smem_desc(bhi, 16, 256, 6) : smem_desc(bhi, 16, 1024, 2);
+          const uint64_t d_blo = tail8 ? smem_desc(bhi + a.w_tile_bytes, 16, 256, 6) : smem_desc(bhi + a.w_tile_bytes, 16, 1024, 2);
           if (ksteps == 4) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -382,7 +394,8 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   a.ring_bytes = rings(a.n_raw, a.n_b) - a.n_raw * a.raw_bytes;   // weight ring, padded when the staging tile needs more
   MFLOW_REQUIRE(total(a.n_raw, a.n_b) <= one_cta_budget, "tile does not fit in shared memory");
 
-  CUtensorMap mx, mhi, mlo, maux, my;
+  CUtensorMap mx, mhi, mlo, mhi8, mlo8, maux, my;
+  { const int tail = a.Cin % kBlockK; a.tail_k8 = (tail > 0 && tail <= 8 && !getenv("MFLOW_CONV_NO_TAIL8")) ? 1 : 0; }
   {  // output, NCHW: box {W, rows, 32 channels, images}
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
@@ -408,6 +421,9 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)w_rows, 1};
     if (!encode(&mhi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
     if (!encode(&mlo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
+    cuuint32_t box8[3] = {8u, (cuuint32_t)w_rows, 1};
+    if (!encode(&mhi8, w_hi, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B)) return MFLOW_E_BADARG;
+    if (!encode(&mlo8, w_lo, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B)) return MFLOW_E_BADARG;
   }
   const int n_tiles = a.imgs_per_tile > 1 ? (B + a.imgs_per_tile - 1) / a.imgs_per_tile : B * (H / a.rows_per_tile);
   dim3 grid(n_tiles, (a.Cout + kTileN - 1) / kTileN);
@@ -417,6 +433,6 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
-  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, maux, my, a);
+  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a);
   return check_launch("conv_tf32x3_kernel");
 }
