@@ -184,7 +184,7 @@ MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, c
  * cuDNN / cuBLAS fp32 wgrad kernels):
  *   g_w[co, ci, ky, kx] = sum_{b,h,w} g_y[b, co, h, w] * (relu_in ? relu(x) : x)[b, ci, h + ky - 1, w + kx - 1]
  * written in the reference's weight layout [c_out, c_in, kernel, kernel].  3xTF32 on tcgen05 with the pixels as the
- * reduction dimension, split over CTAs and reduced deterministically.  height == width in {8, 16, 32};
+ * reduction dimension, split over CTAs and reduced deterministically.  height == width in {4, 8, 16, 32};
  * kernel == 3 needs c_out <= 112.  desc->relu_out, n_pad, k_pad are ignored.
  * workspace: mflow_conv2d_wgrad_workspace_bytes(desc) bytes, no initialisation needed. */
 MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* desc);

@@ -37,7 +37,7 @@ constexpr int kWgThreads = 32 * 14;
 constexpr int kWgBlockPx = 32;                 // pixels per K block
 constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
 constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
-constexpr int kWgRawSlots = 3, kWgQSlots = 3;
+constexpr int kWgRawSlots = 3, kWgQSlots = 3;   // kWgRawSlots: at most (a.n_raw slots are used: 2 when the boxes are large)
 
 struct WgradArgs {
   float* partial;   // [ks][taps][Cin][Cout]
@@ -46,7 +46,8 @@ struct WgradArgs {
   int relu_in;
   int rows;         // image rows per 32-pixel block (32 / W)
   int box_w;        // raw activation box width: W + 8 (3x3, starts 4 pixels left: TMA needs 16-byte aligned starts) or W
-  int raw_bytes;    // one raw activation box [128 ci][rows][box_w] fp32
+  int raw_bytes;    // one raw activation box [images][128 ci][rows][box_w] fp32
+  int n_raw;        // raw-box ring depth (2 or 3)
   int n_tile;       // MMA N extent (output channels of this launch's q tile, multiple of 16, <= 128)
   int blocks_per_img;  // H * W / 32
   int n_blocks;     // B * blocks_per_img
@@ -104,17 +105,18 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      WgRing rp(kWgRawSlots), rq(kWgQSlots);
+      WgRing rp(a.n_raw), rq(kWgQSlots);
       for (int i = 0; i < n_my; ++i, rp.next(), rq.next()) {
         const int blk = blk0 + i;
-        const int b = blk / a.blocks_per_img, r = blk - b * a.blocks_per_img;   // image, 32-pixel block in it
+        // image and 32-pixel block within it; 4x4 maps: one block = two whole images
+        const int b = kW == 4 ? 2 * blk : blk / a.blocks_per_img, r = kW == 4 ? 0 : blk - b * a.blocks_per_img;
         const int h0 = r * a.rows;
         mbar_wait(&rawp_empty[rp.slot], rp.phase ^ 1);
         mbar_expect_tx(&rawp_full[rp.slot], a.raw_bytes);
         tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], pad ? -4 : 0, h0 + (pad ? dy - 1 : 0), p0, b);
         mbar_wait(&q_empty[rq.slot], rq.phase ^ 1);
         mbar_expect_tx(&qraw_full[rq.slot], a.n_tile * kWgBlockPx * 4);
-        tma_load_3d(s_q + rq.slot * 2 * kWgQBytes, &map_g, &qraw_full[rq.slot], r * kWgBlockPx, q0, b);
+        tma_load_3d(s_q + rq.slot * 2 * kWgQBytes, &map_g, &qraw_full[rq.slot], r * kWgBlockPx, q0, b);   // 4x4: box {16 px, n_tile, 2 images}
       }
     }
   } else if (warp == 1) {
@@ -126,7 +128,12 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int i = 0; i < n_my; ++i, rq.next()) {
         mbar_wait(&q_full[rq.slot], rq.phase);
         const uint32_t qhi = smem_u32(s_q + rq.slot * 2 * kWgQBytes);
-        const uint64_t d_qhi = smem_desc(qhi, 16, 1024, 2), d_qlo = smem_desc(qhi + kWgQBytes, 16, 1024, 2);
+        // 8..32-wide maps: one K-major tile [n_tile][128 B], 128B swizzle.  4x4 maps: the TMA box {16 px, n_tile, 2 images}
+        // lands as two tiles [n_tile][64 B] (64B swizzle), k-steps 0,1 in the first image's tile and 2,3 in the second's.
+        auto q_desc = [&](uint32_t base, int kk) -> uint64_t {
+          if (kW == 4) return smem_desc(base + (kk >> 1) * (a.n_tile * 64) + (kk & 1) * 32, 16, 512, 4);
+          return smem_desc(base + kk * 32, 16, 1024, 2);
+        };
 #pragma unroll
         for (int t = 0; t < taps_here; ++t) {
           mbar_wait(&p_full[sp], pp);
@@ -135,9 +142,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const uint32_t phi = tmem_p + sp * 2 * kWgPCols, plo = phi + kWgPCols;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            umma_tf32_ts(acc, phi + kk * 8, d_qhi + 2 * kk, idesc, (i == 0 && kk == 0) ? 0u : 1u);
-            umma_tf32_ts(acc, plo + kk * 8, d_qhi + 2 * kk, idesc, 1);
-            umma_tf32_ts(acc, phi + kk * 8, d_qlo + 2 * kk, idesc, 1);
+            const uint64_t d_qhi = q_desc(qhi, kk), d_qlo = q_desc(qhi + kWgQBytes, kk);
+            umma_tf32_ts(acc, phi + kk * 8, d_qhi, idesc, (i == 0 && kk == 0) ? 0u : 1u);
+            umma_tf32_ts(acc, plo + kk * 8, d_qhi, idesc, 1);
+            umma_tf32_ts(acc, phi + kk * 8, d_qlo, idesc, 1);
           }
           umma_commit(&p_empty[sp]);
           sp ^= 1;
@@ -153,12 +161,14 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int ch = quad * 32 + lane;                          // channel within the p tile = TMEM lane
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t t_p = tmem_p + t_lane + set * 2 * kWgPCols;
-    constexpr int ch_stride = (kWgBlockPx / kW) * (kTaps == 9 ? kW + 8 : kW);   // floats per channel in the raw box
-    WgRing rp(kWgRawSlots);
+
+    WgRing rp(a.n_raw);
     int pp = 0, item = 0;   // phase of this set's stage; running (block, tap) work item: set s takes the items of parity s
     constexpr bool kPad = kTaps == 9;
-    constexpr int kRows = kWgBlockPx / kW, kBoxW = kPad ? kW + 8 : kW;
-    constexpr int kRawVec = kRows * kBoxW / 4;
+    constexpr int kImgs = kW == 4 ? 2 : 1;                       // images per 32-pixel block
+    constexpr int kRows = kWgBlockPx / kW / kImgs, kBoxW = kPad ? kW + 8 : kW;   // rows per image in the block
+    constexpr int kImgVec = kRows * kBoxW / 4;                   // float4s per (image, channel) in the raw box
+    constexpr int kRawVec = kImgs * kImgVec;
     for (int i = 0; i < n_my; ++i, rp.next()) {
       bool loaded = false;
       float raw[kRawVec * 4];
@@ -168,10 +178,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (!loaded) {
           // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
           mbar_wait(&rawp_full[rp.slot], rp.phase);
-          const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + (ch * ch_stride) / 4;
+          const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + ch * kImgVec;   // box [image][channel][row][w]
 #pragma unroll
           for (int j = 0; j < kRawVec; ++j) {
-            const float4 v = src[j];
+            const float4 v = src[(j / kImgVec) * 128 * kImgVec + (j % kImgVec)];
             raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
           }
           loaded = true;
@@ -186,7 +196,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int px = 8 * j + c;
-            float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];
+            float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];   // rows of both images are consecutive in raw[]
             if (a.relu_in) v = fmaxf(v, 0.f);
             h8[c] = wg_trunc(v);
             l8[c] = wg_round(v - h8[c]);
@@ -265,7 +275,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 static int wgrad_splits(const mflow_conv_desc* d) {
   const int n_dy = d->kernel == 3 ? 3 : 1;
   const int tiles = (int)((d->c_in + 127) / 128) * (int)((d->c_out + 127) / 128);
-  const int64_t n_blocks = d->batch * d->height * d->width / kWgBlockPx;
+  const int64_t n_blocks = d->width == 4 ? (d->batch + 1) / 2 : d->batch * d->height * d->width / kWgBlockPx;
   int64_t ks = kNumSMs / (n_dy * tiles);
   if (ks > n_blocks) ks = n_blocks;
   if (ks < 1) ks = 1;
@@ -286,7 +296,7 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
                                                    void* workspace, void* stream) {
   MFLOW_REQUIRE(d && x && g_y && g_w && workspace, "null pointer");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
-  MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8, "width must be 8, 16 or 32");
+  MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
   MFLOW_REQUIRE(d->height == d->width, "square feature maps only");
   MFLOW_REQUIRE(d->c_in >= 1 && d->c_out >= 1 && d->batch >= 1, "bad extents");
   MFLOW_REQUIRE(d->kernel == 1 || d->c_out <= 112, "3x3 weight gradients support at most 112 output channels");
@@ -296,11 +306,13 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   a.B = B; a.Cin = (int)d->c_in; a.Cout = (int)d->c_out; a.H = H; a.W = W;
   a.taps = d->kernel == 3 ? 9 : 1;
   a.relu_in = d->relu_in;
-  a.rows = kWgBlockPx / W;
+  const int imgs = W == 4 ? 2 : 1;            // 4x4 maps: a 32-pixel block is two whole images
+  a.rows = kWgBlockPx / W / imgs;             // rows per image in a block
   a.box_w = a.taps == 9 ? W + 8 : W;
-  a.raw_bytes = 128 * a.rows * a.box_w * 4;
-  a.blocks_per_img = H * W / kWgBlockPx;
-  a.n_blocks = B * a.blocks_per_img;
+  a.raw_bytes = imgs * 128 * a.rows * a.box_w * 4;
+  a.n_raw = a.raw_bytes > 32 * 1024 ? 2 : kWgRawSlots;
+  a.blocks_per_img = W == 4 ? 1 : H * W / kWgBlockPx;
+  a.n_blocks = W == 4 ? (B + 1) / 2 : B * a.blocks_per_img;
   a.n_dy = a.taps == 9 ? 3 : 1;
   const int q_tiles = (a.Cout + 127) / 128, p_tiles = (a.Cin + 127) / 128;
   // one n_tile for the whole launch: a multiple of 16 covering the widest q tile
@@ -313,17 +325,17 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   {  // activations, NCHW: box {box_w, rows, 128 channels, 1 image}; lands as [channel][row][w]
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.rows, 128u, 1u};
+    cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.rows, 128u, (cuuint32_t)imgs};
     if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
   {  // output gradient as [B][Cout][H*W]: box {32 pixels, n_tile channels, 1 image}, 128-byte swizzled K-major rows
     cuuint64_t dims[3] = {(cuuint64_t)H * W, (cuuint64_t)a.Cout, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kWgBlockPx, (cuuint32_t)a.n_tile, 1u};
-    if (!encode(&mg, g_y, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
+    cuuint32_t box[3] = {(cuuint32_t)(kWgBlockPx / imgs), (cuuint32_t)a.n_tile, (cuuint32_t)imgs};
+    if (!encode(&mg, g_y, 3, dims, str, box, imgs == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
   }
   dim3 grid(n_ks, a.n_dy, q_tiles * p_tiles);
-  const size_t smem = (size_t)kWgQSlots * 2 * kWgQBytes + (size_t)kWgRawSlots * a.raw_bytes + 1024;
+  const size_t smem = (size_t)kWgQSlots * 2 * kWgQBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
   const cudaStream_t st = (cudaStream_t)stream;
 #define MFLOW_WGRAD_LAUNCH(WW, TT)                                                                                   \
   do {                                                                                                               \
@@ -335,9 +347,11 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
     wgrad_tf32x3_kernel<WW, TT><<<grid, kWgThreads, smem, st>>>(mx, mg, a);                                          \
   } while (0)
   if (a.taps == 9) {
-    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 9); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 9); else MFLOW_WGRAD_LAUNCH(8, 9);
+    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 9); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 9); else if (W == 8) MFLOW_WGRAD_LAUNCH(8, 9);
+    else MFLOW_WGRAD_LAUNCH(4, 9);
   } else {
-    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 1); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 1); else MFLOW_WGRAD_LAUNCH(8, 1);
+    if (W == 32) MFLOW_WGRAD_LAUNCH(32, 1); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 1); else if (W == 8) MFLOW_WGRAD_LAUNCH(8, 1);
+    else MFLOW_WGRAD_LAUNCH(4, 1);
   }
 #undef MFLOW_WGRAD_LAUNCH
   const int64_t n_out = (int64_t)a.taps * a.Cin * a.Cout;

@@ -10,9 +10,9 @@ class _Config:
     conv_tensor_cores = os.environ.get("MFLOW_CONV_TC", "1") != "0"
     # weight gradients of those convolutions on the tensor cores too; False = cuDNN / cuBLAS fp32 library calls
     conv_wgrad_tensor_cores = os.environ.get("MFLOW_CONV_WGRAD_TC", "1") != "0"
-    # smallest feature-map width that goes to the tensor-core weight-gradient kernel (8, 16 or 32); below it the
+    # smallest feature-map width that goes to the tensor-core weight-gradient kernel (4, 8, 16 or 32); below it the
     # reduction has too few pixel blocks to fill the machine and the library call is as fast
-    conv_wgrad_min_width = int(os.environ.get("MFLOW_CONV_WGRAD_MIN_WIDTH", "8"))
+    conv_wgrad_min_width = int(os.environ.get("MFLOW_CONV_WGRAD_MIN_WIDTH", "4"))
     # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch
     fuse_linear_glue = os.environ.get("MFLOW_FUSE_GLUE", "1") != "0"
     # full_jacobian=True: the reference's Permutation Jacobian is the transpose of the exact one

@@ -264,7 +264,7 @@ def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in):
 
 def conv_wgrad_supported(x, c_out, kernel):
     b, c_in, h, w = x.shape
-    return h == w and w in (8, 16, 32) and w >= config.conv_wgrad_min_width and b >= 1 and (kernel == 1 or c_out <= 112)
+    return h == w and w in (4, 8, 16, 32) and w >= config.conv_wgrad_min_width and b >= 1 and (kernel == 1 or c_out <= 112)
 
 
 def conv_wgrad_tc(g, x, kernel, relu_in):

@@ -105,7 +105,8 @@ def test_channel_sum_matches_fp64_sum(cuda_device, shape):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [(2, 100, 100, 32, 3, True), (3, 100, 100, 16, 3, True), (5, 100, 100, 8, 3, False), (2, 6, 100, 32, 1, False),
                                   (2, 100, 192, 32, 1, True), (3, 100, 384, 16, 1, True), (2, 24, 100, 8, 1, False), (1, 8, 8, 32, 3, False),
-                                  (2, 130, 40, 16, 1, False), (7, 48, 100, 8, 1, True), (1, 1, 1, 8, 3, False)])
+                                  (2, 130, 40, 16, 1, False), (7, 48, 100, 8, 1, True), (1, 1, 1, 8, 3, False), (6, 100, 100, 4, 3, True),
+                                  (5, 48, 100, 4, 1, False), (3, 100, 1536, 4, 1, True), (1, 3, 5, 4, 3, False)])
 def test_wgrad_tensor_core_matches_fp64_autograd(cuda_device, case):
     """mflow_conv2d_wgrad_tf32x3 against the fp64 autograd weight gradient of F.conv2d (reference: nn/resnet.py conv layers)."""
     from manifold_flow.b200 import ops

@@ -185,3 +185,29 @@ def test_jtj_logdet_vs_slogdet_fp64(cuda_device, d, n):
     ref = torch.slogdet(torch.bmm(jac.double().transpose(1, 2), jac.double()))[1]
     got = ops.jtj_logdet(jac.to(cuda_device)).cpu().double()
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,block", [(700, 33, 256), (1024, 256, 256), (300, 5, 128), (256, 7, 256)])
+def test_blocked_tri_solve_matches_library(cuda_device, n, m, block):
+    """ops.tri_solve (wide LULinear inverse, reference lu.py:75-95 uses torch.triangular_solve) against fp64 solves,
+    values and gradients, lower-unit and upper."""
+    from manifold_flow.b200 import ops
+
+    torch.manual_seed(3)
+    lower = (torch.eye(n, device=cuda_device) + 0.05 * torch.randn(n, n, device=cuda_device).tril(-1)).requires_grad_()
+    upper = (torch.diag(torch.rand(n, device=cuda_device) + 0.5) + 0.05 * torch.randn(n, n, device=cuda_device).triu(1)).requires_grad_()
+    rhs = torch.randn(n, m, device=cuda_device, requires_grad=True)
+    out = ops.tri_solve(upper, ops.tri_solve(lower, rhs, upper=False, unit=True, block=block), upper=True, block=block)
+    g = torch.randn_like(out)
+    grads = torch.autograd.grad(out, [lower, upper, rhs], g)
+    l64, u64, r64 = (t.detach().double().requires_grad_() for t in (lower, upper, rhs))
+    ref = torch.linalg.solve_triangular(u64, torch.linalg.solve_triangular(l64, r64, upper=False, unitriangular=True), upper=True)
+    ref_grads = torch.autograd.grad(ref, [l64, u64, r64], g.double())
+    assert ((out.double() - ref).norm() / ref.norm()).item() < 5e-6
+    # only the entries that are parameters matter: strictly lower part of L, upper part (with diagonal) of U
+    masks = [torch.ones(n, n, device=cuda_device).tril(-1), torch.ones(n, n, device=cuda_device).triu(0), None]
+    for got, want, mask in zip(grads, ref_grads, masks):
+        if mask is not None:
+            got, want = got * mask, want * mask
+        assert ((got.double() - want).norm() / want.norm()).item() < 2e-5

@@ -10,7 +10,7 @@ def ref64(g,x,k,relu):
     w=torch.zeros(g.shape[1],x.shape[1],k,k,device=dev,dtype=torch.float64,requires_grad=True)
     xin=(F.relu(x) if relu else x).double()
     y=F.conv2d(xin,w,padding=k//2); y.backward(g.double()); return w.grad
-cases=[(2,100,100,32,3,True),(3,100,100,16,3,True),(5,100,100,8,3,False),(2,6,100,32,1,False),(2,100,192,32,1,True),(3,100,384,16,1,True),(2,24,100,8,1,False),(1,8,8,32,3,False),(2,130,40,16,1,False)]
+cases=[(2,100,100,32,3,True),(3,100,100,16,3,True),(5,100,100,8,3,False),(2,6,100,32,1,False),(2,100,192,32,1,True),(3,100,384,16,1,True),(2,24,100,8,1,False),(1,8,8,32,3,False),(2,130,40,16,1,False),(6,100,100,4,3,True),(5,48,100,4,1,False),(3,100,1536,4,1,True)]
 if len(sys.argv)>1: cases=[cases[int(sys.argv[1])]]
 TIMING=len(sys.argv)<=1
 for (B,ci,co,HW,k,relu) in cases:
@@ -30,7 +30,7 @@ def timeit(fn,iters=5):
     e0.record()
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)/iters*1e3
-for (B,ci,co,HW,k) in [] if not TIMING else [(256,100,100,32,3),(256,100,192,32,1),(256,6,100,32,1),(256,100,100,16,3),(256,100,384,16,1),(256,100,100,8,3)]:
+for (B,ci,co,HW,k) in [] if not TIMING else [(256,100,100,32,3),(256,100,192,32,1),(256,6,100,32,1),(256,100,100,16,3),(256,100,384,16,1),(256,100,100,8,3),(256,100,100,4,3),(256,100,1536,4,1)]:
     x=torch.randn(B,ci,HW,HW,device=dev); g=torch.randn(B,co,HW,HW,device=dev); w0=torch.zeros(co,ci,k,k,device=dev)
     t_tc=timeit(lambda: ops.conv_wgrad_tc(g,x,k,True))
     t_lib=timeit(lambda: torch.ops.aten.convolution_backward(g,F.relu(x),w0,None,[1,1],[k//2]*2,[1,1],False,[0,0],1,[False,True,False]))
