@@ -80,6 +80,10 @@ __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((_
 // [0][s] transform start (stage free), [1][s] transform done, [2][s] MMA issue (operands ready), [3][s] raw box ready (per kb),
 // [4][0] kernel start, [4][1] accumulator complete, [4][2] epilogue done
 __device__ long long g_conv_trace[5][64];
+// ... and every CTA of grid row 0 records {globaltimer at entry, at exit, SM id} (first 4096 CTAs)
+__device__ unsigned long long g_conv_cta[4096][3];
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int sm_id() { unsigned int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 
 // ring cursor without divisions: slot index + phase parity
 struct Ring {
@@ -116,6 +120,10 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #define s_tmem (*s_tmem_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((a.debug & 8) && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 4096) {
+    g_conv_cta[blockIdx.x][0] = global_ns();
+    g_conv_cta[blockIdx.x][2] = sm_id();
+  }
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * kTileN;
   const int tiles_per_img = a.imgs_per_tile > 1 ? 1 : a.H / a.rows_per_tile;
@@ -133,24 +141,56 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_init(&acc_full, 1);
     mbar_init(&aux_full, 1);
     fence_barrier_init();
+    // First loads before the TMEM allocation and the CTA-wide barrier (the barriers they signal were initialised by
+    // this very thread): the first raw box(es) and as many weight tiles of channel block 0 as the ring holds.
+    // The producer loop below skips exactly these.
+    {
+      const int n_raw_pre = (a.n_raw >= 2 && a.k_blocks >= 2) ? 2 : 1;
+      for (int kb = 0; kb < n_raw_pre; ++kb) {
+        mbar_expect_tx(&raw_full[kb], a.raw_tx);
+        tma_load_4d(s_raw + kb * a.raw_bytes, &map_x, &raw_full[kb], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+      }
+      const int n_w_pre = min(a.n_b, a.taps);
+      const bool t8 = a.tail_k8 && a.k_blocks == 1;
+      for (int tap = 0; tap < n_w_pre; ++tap) {
+        uint8_t* dst = s_b + tap * 2 * a.w_tile_bytes;
+        mbar_expect_tx(&b_full[tap], t8 ? a.w_tile_bytes / 2 : 2 * a.w_tile_bytes);
+        tma_load_3d(dst, t8 ? &map_whi8 : &map_whi, &b_full[tap], 0, n0, tap);
+        tma_load_3d(dst + a.w_tile_bytes, t8 ? &map_wlo8 : &map_wlo, &b_full[tap], 0, n0, tap);
+      }
+    }
   }
   if (warp == 1) tmem_alloc(&s_tmem, kTmemCols);  // [0,128) accumulator, then kStagesA x {A_hi, A_lo} x 32 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const bool trace = (a.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool trace = (a.debug & 8) && blockIdx.x == (unsigned)(a.debug >> 8) && blockIdx.y == 0;   // traced CTA: debug >> 8
   if (trace && threadIdx.x == 0) g_conv_trace[4][0] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
       Ring rb(a.n_raw), sb(a.n_b);
-      for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
-        mbar_wait(&raw_empty[rb.slot], rb.phase ^ 1);
-        mbar_expect_tx(&raw_full[rb.slot], a.raw_tx);
-        tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+      // With two raw slots the boxes run one channel block ahead of the weight tiles: the box of block kb + 1 is
+      // requested before the nine weight tiles of block kb (its slot was freed by block kb - 1).  Requested after
+      // them it arrived ~1500 cycles late at every block boundary (step trace), in both co-resident CTAs at once.
+      const bool ahead = a.n_raw >= 2;
+      const int n_raw_pre = (a.n_raw >= 2 && a.k_blocks >= 2) ? 2 : 1, n_w_pre = min(a.n_b, a.taps);   // issued before the CTA barrier
+      auto load_raw = [&](int kb) {
+        if (kb >= n_raw_pre) {
+          mbar_wait(&raw_empty[rb.slot], rb.phase ^ 1);
+          mbar_expect_tx(&raw_full[rb.slot], a.raw_tx);
+          tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+        }
+        rb.next();
+      };
+      if (ahead) load_raw(0);
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        if (!ahead) load_raw(kb);
+        else if (kb + 1 < a.k_blocks) load_raw(kb + 1);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
+          if (kb == 0 && tap < n_w_pre) continue;
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
           if (a.tail_k8 && kb == a.k_blocks - 1) {
             // last channel block with at most 8 channels: 32-byte rows (32B swizzle) instead of 128-byte ones -
@@ -312,6 +352,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   if (trace && threadIdx.x == 0) g_conv_trace[4][2] = clock64();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+  if ((a.debug & 8) && threadIdx.x == 32 && blockIdx.y == 0 && blockIdx.x < 4096) g_conv_cta[blockIdx.x][1] = global_ns();
 }
 #undef acc_full
 #undef aux_full
@@ -324,6 +365,9 @@ constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kStagesA 
 using namespace mflow;
 
 // debugging aid, not part of the ABI: copy out the step trace written under MFLOW_CONV_DEBUG=8
+extern "C" MFLOW_API int mflow_debug_conv_ctas(unsigned long long* out12288) {
+  return cudaMemcpyFromSymbol(out12288, g_conv_cta, sizeof(unsigned long long) * 4096 * 3) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+}
 extern "C" MFLOW_API int mflow_debug_conv_trace(long long* out320) {
   return cudaMemcpyFromSymbol(out320, g_conv_trace, sizeof(long long) * 5 * 64) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
 }

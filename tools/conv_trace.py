@@ -1,6 +1,6 @@
 """Per-step timeline of one CTA of the tcgen05 convolution (MFLOW_CONV_DEBUG=8): cycles relative to kernel start."""
 import sys, os, ctypes
-os.environ['MFLOW_CONV_DEBUG'] = '8'
+os.environ['MFLOW_CONV_DEBUG'] = str(8 + 256 * int(sys.argv[3] if len(sys.argv) > 3 else 0))   # traced CTA index in the high bits
 R=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ('manifold-flow_b200','oracle','tests',''): sys.path.insert(0, os.path.join(R,p))
 import torch
@@ -28,3 +28,21 @@ for s in range(36):
     a,bb,c=t[0][s]-t0,t[1][s]-t0,t[2][s]-t0
     print(f'{s:3d}: {a:7d} {bb:7d} ({bb-a:5d}) | {c:7d} | {"" if prev is None else c-prev}')
     prev=c
+
+# per-SM CTA timeline (globaltimer, ns)
+import collections
+L.mflow_debug_conv_ctas.restype=ctypes.c_int; L.mflow_debug_conv_ctas.argtypes=[ctypes.c_void_p]
+buf=(ctypes.c_ulonglong*(4096*3))(); L.mflow_debug_conv_ctas(buf)
+n_cta=min(4096, (B*HW*HW+127)//128)
+recs=[(buf[3*i],buf[3*i+1],buf[3*i+2]) for i in range(n_cta)]
+t_min=min(r[0] for r in recs); t_max=max(r[1] for r in recs)
+dur=[r[1]-r[0] for r in recs]
+print(f'CTAs {n_cta}: kernel span {(t_max-t_min)/1e3:.1f} us; CTA duration mean {sum(dur)/len(dur)/1e3:.2f} us, min {min(dur)/1e3:.2f}, max {max(dur)/1e3:.2f}')
+by_sm=collections.defaultdict(list)
+for s0,e0,sm in recs: by_sm[sm].append((s0-t_min,e0-t_min))
+sm0=sorted(by_sm)[0]
+print(f'SM {sm0}: {len(by_sm[sm0])} CTAs; (start,end) us:', [(round(a/1e3,1),round(b/1e3,1)) for a,b in sorted(by_sm[sm0])])
+busy=[]
+for sm,l in by_sm.items():
+    l.sort(); busy.append(sum(b-a for a,b in l))
+print(f'mean CTA-time per SM {sum(busy)/len(busy)/1e3:.1f} us over {len(by_sm)} SMs (2 CTAs run concurrently)')
