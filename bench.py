@@ -414,7 +414,7 @@ def run_b200(args):
             "dtype": "f32" if config.conditioner_math == "fp32" else "f32 (tf32 conditioner GEMMs)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * b, "per_gpu_batch": b, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations + spline parameters, several GB) exceeds the 126 MB L2; 4 input batches rotate",
-                       "conditioner": ("image convolutions forward, data gradient and weight gradient: tcgen05 3xTF32 kernels of libmflow_b200 (4x4 feature maps' weight gradients: cuDNN); vector-conditioner GEMMs and the 3840-wide LU layers: cuBLAS fp32"
+                       "conditioner": ("image convolutions forward, data gradient and weight gradient: tcgen05 3xTF32 kernels of libmflow_b200; vector-conditioner GEMMs (256 rows: below the tensor-core threshold) and the 3840-wide LU layers: cuBLAS fp32 GEMMs (LU inverse: blocked substitution)"
                                        if config.conv_tensor_cores else "cuBLAS/cuDNN fp32 library calls")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_secs / args.steps},

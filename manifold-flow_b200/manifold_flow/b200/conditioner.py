@@ -3,9 +3,10 @@
 Image conditioners (``ConvResidualNet``): every 3x3 / 1x1 convolution - forward and data gradient - runs
 on the tcgen05 tensor cores through ``mflow_conv2d_tf32x3`` (TMA-fed implicit GEMM on NCHW tensors,
 3xTF32 split for fp32 accuracy, pre-activation ReLU, bias, residual add and the ReLU mask of the backward
-pass fused).  Still library calls in this round: the weight gradients of those convolutions (cuDNN), the
-small vector conditioners (``ResidualNet``: cuBLAS GEMMs with M = batch) and the GLU context path; TF32 is
-switched off around them unless ``config.conditioner_math == "tf32"``.
+pass fused); their weight gradients through ``mflow_conv2d_wgrad_tf32x3``.  Vector conditioners (``ResidualNet``)
+take the same kernels from ``config.linear_tc_min_rows`` rows on (``residual_net_planes``); below that they are
+cuBLAS GEMMs with M = batch (launch-latency bound either way), with TF32 switched off unless
+``config.conditioner_math == "tf32"``.
 """
 import contextlib
 
@@ -56,6 +57,40 @@ def residual_block_linear(x, lin0, lin1, gate_layer, context):
         if gate_layer is not None:
             t = F.glu(torch.cat((t, F.linear(context, gate_layer.weight, gate_layer.bias)), dim=1), dim=1)
         return x + t
+
+
+def residual_net_planes(net, inputs, context):
+    """ResidualNet (nn/resnet.py:43-72) on the tensor-core convolution kernels, or None when the shape does not qualify.
+
+    The batch rows become the pixels of [rows / w^2, C, w, w] tensors (one blocked transposition in, one out); every
+    Linear layer is then a 1x1 convolution with the pre-activation ReLU, the bias and the skip connection fused,
+    its data gradient runs through the same kernel and its weight gradient through the pixels-as-K kernel."""
+    rows = inputs.shape[0]
+    if not (config.conv_tensor_cores and config.conditioner_math == "fp32" and inputs.dim() == 2 and rows >= config.linear_tc_min_rows):
+        return None
+    w = next((c for c in (32, 16, 8, 4) if rows % (c * c) == 0), 0)
+    if not w:
+        return None
+    require_cuda(inputs)
+
+    def to_planes(t):
+        return t.reshape(rows // (w * w), w * w, t.shape[1]).transpose(1, 2).contiguous().view(-1, t.shape[1], w, w)
+
+    def lin(x, layer, **kw):
+        weight = layer.weight
+        return ops.conv_tc(x, weight.view(weight.shape[0], weight.shape[1], 1, 1), layer.bias, weight_owner=weight, **kw)
+
+    h = lin(to_planes(inputs if context is None else torch.cat((inputs, context), dim=1)), net.initial_layer)
+    ctx_planes = None if context is None else to_planes(context)
+    for block in net.blocks:
+        lin0, lin1 = block.linear_layers
+        t = lin(h, lin0, relu_in=True)
+        if context is None:
+            h = lin(t, lin1, relu_in=True, residual=h)
+        else:  # glu(cat(t, gate)) = t * sigmoid(gate)   resnet.py:38-39
+            h = h + lin(t, lin1, relu_in=True) * torch.sigmoid(lin(ctx_planes, block.context_layer))
+    out = lin(h, net.final_layer)
+    return out.view(out.shape[0], out.shape[1], w * w).transpose(1, 2).reshape(rows, out.shape[1])
 
 
 def residual_block_conv(x, conv0, conv1, gate_layer, context):

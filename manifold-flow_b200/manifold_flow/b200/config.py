@@ -13,6 +13,10 @@ class _Config:
     # smallest feature-map width that goes to the tensor-core weight-gradient kernel (4, 8, 16 or 32); below it the
     # reduction has too few pixel blocks to fill the machine and the library call is as fast
     conv_wgrad_min_width = int(os.environ.get("MFLOW_CONV_WGRAD_MIN_WIDTH", "4"))
+    # vector conditioners (ResidualNet): from this many rows on, the whole net runs on the tensor-core convolution
+    # kernels (a Linear layer is a 1x1 convolution once the batch rows are laid out as pixels); below it the
+    # 2-CTA launches are latency bound and the cuBLAS sgemm calls are faster
+    linear_tc_min_rows = int(os.environ.get("MFLOW_LINEAR_TC_MIN_ROWS", "32768"))
     # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch
     fuse_linear_glue = os.environ.get("MFLOW_FUSE_GLUE", "1") != "0"
     # full_jacobian=True: the reference's Permutation Jacobian is the transpose of the exact one

@@ -224,11 +224,14 @@ class _WeightCache:
     def __init__(self):
         self._entries = {}
 
-    def get(self, weight, transposed):
-        key = (id(weight), transposed)
-        ver = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    def get(self, weight, transposed, owner=None):
+        """owner: the long-lived tensor (parameter) that `weight` is a fresh view of, if any - the entry is then
+        bound to the owner, so that a new view object per call does not miss."""
+        anchor = weight if owner is None else owner
+        key = (id(anchor), transposed)
+        ver = (weight.data_ptr(), anchor._version, tuple(weight.shape))
         ent = self._entries.get(key)
-        if ent is None or ent[0]() is not weight or ent[1] != ver:
+        if ent is None or ent[0]() is not anchor or ent[1] != ver:
             if len(self._entries) > 4096:
                 self._entries = {k: v for k, v in self._entries.items() if v[0]() is not None}
             with torch.no_grad():
@@ -237,7 +240,7 @@ class _WeightCache:
                     taps = weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
                 else:  # data gradient: correlation with the taps flipped and channels swapped
                     taps = weight.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
-                ent = (weakref.ref(weight), ver, _split_weight(taps))
+                ent = (weakref.ref(anchor), ver, _split_weight(taps))
             self._entries[key] = ent
         return ent[2]
 
@@ -292,12 +295,13 @@ class _ConvTC(torch.autograd.Function):
     epilogue); weight gradient as a library call (cuDNN) for now; bias gradient a reduction."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu_in):
+    def forward(ctx, x, weight, bias, residual, relu_in, owner=None):
         require_cuda(x, weight, bias, residual)
         x = _c(x)
         residual = None if residual is None else _c(residual)
         kernel = weight.shape[2]
-        y = _conv_tc_launch(x, _weight_cache.get(weight, False), weight.shape[0], kernel, bias, residual, None, relu_in)
+        y = _conv_tc_launch(x, _weight_cache.get(weight, False, owner), weight.shape[0], kernel, bias, residual, None, relu_in)
+        ctx.owner = owner
         ctx.save_for_backward(x, weight)
         ctx.relu_in, ctx.has_bias, ctx.has_res = relu_in, bias is not None, residual is not None
         return y
@@ -309,7 +313,7 @@ class _ConvTC(torch.autograd.Function):
         gx = gw = gb = None
         kernel = weight.shape[2]
         if ctx.needs_input_grad[0]:
-            gx = _conv_tc_launch(g, _weight_cache.get(weight, True), weight.shape[1], kernel, None, None, x if ctx.relu_in else None, False)
+            gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner), weight.shape[1], kernel, None, None, x if ctx.relu_in else None, False)
         if ctx.needs_input_grad[1] and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
             gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in)
         elif ctx.needs_input_grad[1]:   # shapes the tensor-core kernel does not take (4x4 maps): library call
@@ -318,7 +322,7 @@ class _ConvTC(torch.autograd.Function):
                                                      [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = channel_sum(g)
-        return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None
+        return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -395,8 +399,8 @@ def channel_sum(x):
     return out
 
 
-def conv_tc(x, weight, bias=None, residual=None, relu_in=False):
-    return _ConvTC.apply(x, weight, bias, residual, bool(relu_in))
+def conv_tc(x, weight, bias=None, residual=None, relu_in=False, weight_owner=None):
+    return _ConvTC.apply(x, weight, bias, residual, bool(relu_in), weight_owner)
 
 
 # --------------------------------------------------------------------------------------------

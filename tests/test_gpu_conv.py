@@ -123,3 +123,53 @@ def test_wgrad_tensor_core_matches_fp64_autograd(cuda_device, case):
     rel = ((got.double() - w.grad).norm() / w.grad.norm()).item()
     assert rel < 2e-6, rel                                   # fp32 library wgrad sits at 1e-7 .. 2e-6 on these
     assert torch.equal(got, ops.conv_wgrad_tc(g, x, k, relu))   # deterministic
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,n_in,n_out,ctx", [(4096, 20, 640, None), (8192, 7, 224, 2), (1024, 33, 96, 1), (4112, 3, 23, None)])
+def test_residual_net_tensor_core_path_matches_fp64(cuda_device, rows, n_in, n_out, ctx):
+    """ResidualNet (reference nn/resnet.py:43-72) through the tcgen05 convolution kernels (batch rows as pixels) against
+    an fp64 evaluation of the same formulas: outputs and all gradients.  Rows in which some pre-activation lies within
+    1e-4 of the ReLU kink get a zero incoming gradient: there the fp32 and fp64 masks may legitimately differ (one such
+    element among 400k changes the weight gradients by 1e-3)."""
+    from manifold_flow import nn as nn_
+    from manifold_flow.b200.config import config
+
+    torch.manual_seed(17)
+    net = nn_.ResidualNet(n_in, n_out, hidden_features=100, context_features=ctx, num_blocks=2).to(cuda_device)
+    for p in net.parameters():   # the last layer of each block is initialised to ~0 (resnet.py:23-25): make every path matter
+        p.data.normal_(0.0, 0.2)
+    x = torch.randn(rows, n_in, device=cuda_device, requires_grad=True)
+    c = None if ctx is None else torch.randn(rows, ctx, device=cuda_device)
+    g = torch.randn(rows, n_out, device=cuda_device)
+
+    P = {n: p.detach().double().requires_grad_() for n, p in net.named_parameters()}
+    x64 = x.detach().double().requires_grad_()
+    c64 = None if c is None else c.double()
+    h = F.linear(x64 if c is None else torch.cat((x64, c64), 1), P["initial_layer.weight"], P["initial_layer.bias"])
+    near_kink = torch.zeros(rows, dtype=torch.bool, device=cuda_device)
+    for i in range(2):
+        near_kink |= h.detach().abs().min(dim=1).values < 1e-4
+        t = F.linear(F.relu(h), P[f"blocks.{i}.linear_layers.0.weight"], P[f"blocks.{i}.linear_layers.0.bias"])
+        near_kink |= t.detach().abs().min(dim=1).values < 1e-4
+        t = F.linear(F.relu(t), P[f"blocks.{i}.linear_layers.1.weight"], P[f"blocks.{i}.linear_layers.1.bias"])
+        if c is not None:
+            t = t * torch.sigmoid(F.linear(c64, P[f"blocks.{i}.context_layer.weight"], P[f"blocks.{i}.context_layer.bias"]))
+        h = h + t
+    y64 = F.linear(h, P["final_layer.weight"], P["final_layer.bias"])
+    g = g * (~near_kink)[:, None]
+    assert near_kink.float().mean().item() < 0.2
+    y64.backward(g.double())
+
+    old = config.linear_tc_min_rows
+    try:
+        config.linear_tc_min_rows = 1
+        y = net(x, c)
+        y.backward(g)
+    finally:
+        config.linear_tc_min_rows = old
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(y, y64.detach()) < 1e-5
+    assert rel(x.grad, x64.grad) < 2e-5
+    for n, p in net.named_parameters():
+        assert rel(p.grad, P[n].grad) < 2e-5, n
