@@ -186,10 +186,15 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         rb.next();
       };
       if (ahead) load_raw(0);
+      // The producer issues in program order, so a wait blocks everything behind it: the box of block kb + 1 (whose
+      // slot frees up only when block kb - 1 is fully transformed) goes out AFTER the first weight tiles of block kb,
+      // which would otherwise arrive ~4500 cycles late at every block boundary (step trace).
+      // (1x1 convolutions have one weight tile per block and live off the boxes: there the box goes first.)
       for (int kb = 0; kb < a.k_blocks; ++kb) {
         if (!ahead) load_raw(kb);
-        else if (kb + 1 < a.k_blocks) load_raw(kb + 1);
+        else if (a.taps == 1 && kb + 1 < a.k_blocks) load_raw(kb + 1);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
+          if (ahead && a.taps > 1 && tap == 2 && kb + 1 < a.k_blocks) load_raw(kb + 1);
           if (kb == 0 && tap < n_w_pre) continue;
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
           if (a.tail_k8 && kb == a.k_blocks - 1) {
