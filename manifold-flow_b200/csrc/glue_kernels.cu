@@ -97,6 +97,64 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
   }
 }
 
+// Planes layout (image levels: [B, 12, 32, 32] ... [B, 96, 4, 4]): a thread owns PX consecutive pixels of one sample,
+// keeps all C input channels of them in registers (C coalesced loads in flight per thread) and produces C / CG of
+// the outputs from the matrix in shared memory (broadcast 16-byte loads); the CG threads of a pixel group re-read the
+// same inputs through L1.  One read and one write of the activation, nothing staged: the HBM-bound form.
+template <int PX> struct MixVec;
+template <> struct MixVec<4> { using T = float4; };
+template <> struct MixVec<2> { using T = float2; };
+template <> struct MixVec<1> { using T = float; };
+template <int C, int PX, int CG>
+__global__ void __launch_bounds__(256) chanmix_planes_kernel(const float* __restrict__ x, const float* __restrict__ mat,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int64_t n_outer, int64_t I, int64_t x_so, int64_t y_so) {
+  using V = typename MixVec<PX>::T;
+  __shared__ __align__(16) float s_mat[C * C];
+  __shared__ float s_b[C];
+  for (int idx = threadIdx.x; idx < C * C; idx += 256) s_mat[idx] = mat[idx];
+  for (int idx = threadIdx.x; idx < C; idx += 256) s_b[idx] = bias ? bias[idx] : 0.f;
+  __syncthreads();
+  const int64_t ivn = I / PX, total = n_outer * ivn * CG;
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
+    const int cg = (int)(q % CG);
+    const int64_t qq = q / CG, o = qq / ivn, iv = qq - o * ivn;
+    const V* xp = reinterpret_cast<const V*>(x + o * x_so) + iv;
+    V* yp = reinterpret_cast<V*>(y + o * y_so) + iv;
+    float v[C][PX];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const V t = __ldg(xp + k * ivn);
+      const float* tf = reinterpret_cast<const float*>(&t);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) v[k][p] = tf[p];
+    }
+#pragma unroll 2
+    for (int cc = 0; cc < C / CG; ++cc) {
+      const int c = cg * (C / CG) + cc;
+      float acc[PX];
+#pragma unroll
+      for (int p = 0; p < PX; ++p) acc[p] = s_b[c];
+#pragma unroll
+      for (int k4 = 0; k4 < C / 4; ++k4) {
+        const float4 m = *reinterpret_cast<const float4*>(s_mat + c * C + 4 * k4);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          acc[p] = fmaf(m.x, v[4 * k4][p], acc[p]);
+          acc[p] = fmaf(m.y, v[4 * k4 + 1][p], acc[p]);
+          acc[p] = fmaf(m.z, v[4 * k4 + 2][p], acc[p]);
+          acc[p] = fmaf(m.w, v[4 * k4 + 3][p], acc[p]);
+        }
+      }
+      V out;
+      float* of = reinterpret_cast<float*>(&out);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) of[p] = acc[p];
+      yp[c * ivn] = out;
+    }
+  }
+}
+
 // g_mat[c,k] = sum_q g_y[c,q] x[k,q],  g_bias[c] = sum_q g_y[c,q]: each CTA accumulates a slab of
 // pixels into shared memory and writes its partial [C*C + C] block; a second kernel adds the partials in a
 // fixed order (deterministic).  (One CTA summing all partials at the end capped the grid at a few dozen CTAs
@@ -384,6 +442,20 @@ extern "C" MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* d, const floa
   const int64_t n_pix = d->n_outer * d->n_inner;
   if (n_pix == 0) return MFLOW_OK;
   const int C = (int)d->n_chan;
+  // planes layout, 16-byte aligned rows, the image levels' channel counts: the register-resident kernel
+  if ((C == 12 || C == 24 || C == 48) && d->x_si == 1 && d->y_si == 1 && d->x_sc == d->n_inner && d->y_sc == d->n_inner &&
+      d->n_inner % 4 == 0 && d->x_so % 4 == 0 && d->y_so % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
+    const cudaStream_t st = (cudaStream_t)stream;
+    auto grid_of = [&](int px, int cgroups) {
+      int64_t g = (d->n_outer * (d->n_inner / px) * cgroups + 255) / 256;
+      return (unsigned)(g > 8 * kNumSMs ? 8 * kNumSMs : g);
+    };
+    if (C == 12) chanmix_planes_kernel<12, 4, 1><<<grid_of(4, 1), 256, 0, st>>>(x, mat, bias, y, d->n_outer, d->n_inner, d->x_so, d->y_so);
+    else if (C == 24) chanmix_planes_kernel<24, 4, 1><<<grid_of(4, 1), 256, 0, st>>>(x, mat, bias, y, d->n_outer, d->n_inner, d->x_so, d->y_so);
+    else chanmix_planes_kernel<48, 2, 2><<<grid_of(2, 2), 256, 0, st>>>(x, mat, bias, y, d->n_outer, d->n_inner, d->x_so, d->y_so);
+    // (96 channels, 4x4 maps: 16 pixels per image - the tiled kernel below is faster there: 24 vs 43 us)
+    return check_launch("chanmix_planes_kernel");
+  }
   const size_t smem = mix_smem(C);
   if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
