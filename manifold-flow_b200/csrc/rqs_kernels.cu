@@ -59,7 +59,7 @@ constexpr int64_t kCounterBytes = 65536 * 4;  // one arrival counter per sample 
 // INNER > 0: the standard planes layout with a compile-time plane size (p_si == 1, p_sp == INNER, p_sc ==
 // P * INNER): parameter loads become LDG [base + immediate] with no per-load address arithmetic.
 template <int K, bool INV, int INNER>
-__global__ void __launch_bounds__(kPlaneThreads, 4) rqs_planes_apply_kernel(const RqsArgs a) {
+__global__ void __launch_bounds__(kPlaneThreads, 6) rqs_planes_apply_kernel(const RqsArgs a) {
   constexpr int P = 3 * K - 1;
   __shared__ float red[kPlaneThreads / 32];
   __shared__ int s_last;
