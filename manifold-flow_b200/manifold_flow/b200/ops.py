@@ -348,16 +348,17 @@ def _blocked_trisolve(mat, rhs, upper, unit, block):
         s0 = starts[-1]
         tail = mat[s0:, s0:]
         dinv[-1] = torch.linalg.solve_triangular(tail, torch.eye(n - s0, dtype=mat.dtype, device=mat.device), upper=upper, unitriangular=unit)
+    out = torch.empty_like(x)   # solved blocks land here; x keeps the running right-hand side
     order = range(len(starts) - 1, -1, -1) if upper else range(len(starts))
     for i in order:
         lo, hi = starts[i], min(starts[i] + block, n)
-        xi = dinv[i] @ x[lo:hi]
-        x[lo:hi] = xi
+        xi = out[lo:hi]
+        torch.mm(dinv[i], x[lo:hi], out=xi)
         if upper and lo > 0:
             x[:lo].addmm_(mat[:lo, lo:hi], xi, alpha=-1.0)
         elif not upper and hi < n:
             x[hi:].addmm_(mat[hi:, lo:hi], xi, alpha=-1.0)
-    return x
+    return out
 
 
 class _TriSolve(torch.autograd.Function):
