@@ -378,7 +378,8 @@ def run_b200(args):
                     "achieved": ach, "peak": tc_peak, "peak_source": tc_src, "unit": "TFLOP/s", "frac": ach / tc_peak if ach else None,
                     "traffic": 167.44e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one level-0 3x3 launch (B=256, 100->100, 32x32) from the ncu --set full capture in profiles/r1_conv_tf32x3_ncu_full.md; algorithmic 209.7e6 (part of the output is still in L2 when the kernel ends)",
                     "share_of_step": (cms / 2) / step_ms,
-                    "note": "achieved counts useful fp32-equivalent FLOPs; the tensor pipe executes 3x that in TF32 (nominal TF32 peak is half the bf16 peak)",
+                    "tensor_pipe_active_ncu": 0.697, "tf32_passes_per_useful_flop": 3,
+                    "note": "achieved counts useful fp32-equivalent FLOPs; the tensor pipe executes 3x that in TF32 (nominal TF32 peak is half the bf16 peak); tensor_pipe_active_ncu = sm__pipe_tensor_cycles_active of the level-0 3x3 launch (profiles/r1_conv_tf32x3_ncu_full.md)",
                     "per_kernel": {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
                                        "useful_TFLOPs": v["bytes"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None} for k, v in conv.items()},
                     "secondary": spline}
