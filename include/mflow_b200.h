@@ -186,10 +186,12 @@ MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, c
  * written in the reference's weight layout [c_out, c_in, kernel, kernel].  3xTF32 on tcgen05 with the pixels as the
  * reduction dimension, split over CTAs and reduced deterministically.  height == width in {4, 8, 16, 32};
  * kernel == 3 needs c_out <= 112.  desc->relu_out, n_pad, k_pad are ignored.
+ * g_bias (optional, [c_out]): the bias gradient sum_{b,h,w} g_y[b, co, h, w], accumulated by the warps that
+ * already touch every element of g_y (plain fp32 sums, deterministic).
  * workspace: mflow_conv2d_wgrad_workspace_bytes(desc) bytes, no initialisation needed. */
 MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* desc);
 MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* desc, const float* x, const float* g_y, float* g_w,
-                              void* workspace, void* stream);
+                              float* g_bias, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Likelihood epilogues.

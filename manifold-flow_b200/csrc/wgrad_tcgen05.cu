@@ -41,6 +41,7 @@ constexpr int kWgRawSlots = 3, kWgQSlots = 3;   // kWgRawSlots: at most (a.n_raw
 
 struct WgradArgs {
   float* partial;   // [ks][taps][Cin][Cout]
+  float* bias_partial;   // [ks][Cout] or null: per-split sums of g_y over the pixels (the bias gradient comes for free)
   int B, Cin, Cout, H, W;
   int taps;         // 9 or 1
   int relu_in;
@@ -233,24 +234,57 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
   } else {
     // ===== Q split: the TMA-loaded fp32 tile becomes its TF32 hi part in place, the lo part goes next to it =====
+    // These threads see every element of g_y exactly once, so the kernel-row-1 CTA of input-channel tile 0 also
+    // accumulates the bias gradient sum_pixels g_y[co] (a thread's float4 positions are the same in every block).
     const int tid = threadIdx.x - 320;   // 0..127
     WgRing rq(kWgQSlots);
     const int n_vec = a.n_tile * (kWgBlockPx / 4);   // float4s of the tile
+    const bool do_bias = a.bias_partial != nullptr && dy == (kTaps == 9 ? 1 : 0) && p0 == 0;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // n_vec <= 1024 = 8 x 128
+    int last_slot = 0;
     for (int i = 0; i < n_my; ++i, rq.next()) {
       mbar_wait(&qraw_full[rq.slot], rq.phase);
       float4* hi = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes);
       float4* lo = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes + kWgQBytes);
-      for (int j = tid; j < n_vec; j += 128) {
-        const float4 v = hi[j];
-        float4 h, l;
-        h.x = wg_trunc(v.x); h.y = wg_trunc(v.y); h.z = wg_trunc(v.z); h.w = wg_trunc(v.w);
-        l.x = wg_round(v.x - h.x); l.y = wg_round(v.y - h.y); l.z = wg_round(v.z - h.z); l.w = wg_round(v.w - h.w);
-        hi[j] = h;
-        lo[j] = l;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = tid + 128 * k;
+        if (j < n_vec) {
+          const float4 v = hi[j];
+          bsum[k] += (v.x + v.y) + (v.z + v.w);
+          float4 h, l;
+          h.x = wg_trunc(v.x); h.y = wg_trunc(v.y); h.z = wg_trunc(v.z); h.w = wg_trunc(v.w);
+          l.x = wg_round(v.x - h.x); l.y = wg_round(v.y - h.y); l.z = wg_round(v.z - h.z); l.w = wg_round(v.w - h.w);
+          hi[j] = h;
+          lo[j] = l;
+        }
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full[rq.slot]);
+      last_slot = rq.slot;
+    }
+    if (do_bias) {
+      // per-thread sums -> per-channel sums in a fixed order, through the (drained) Q ring
+      mbar_wait(&acc_full, 0);                       // all MMAs have read the ring
+      float* scratch = reinterpret_cast<float*>(s_q);
+      (void)last_slot;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = tid + 128 * k;
+        if (j < n_vec) scratch[j] = bsum[k];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // the four Q-split warps
+      if (tid < a.n_tile && q0 + tid < a.Cout) {
+        float t = 0.f;
+        if (kW == 4) {   // two tiles [n_tile][4 float4]: image 0 then image 1
+          for (int e = 0; e < 4; ++e) t += scratch[tid * 4 + e];
+          for (int e = 0; e < 4; ++e) t += scratch[a.n_tile * 4 + tid * 4 + e];
+        } else {         // one tile [n_tile][8 float4] (the 128B swizzle permutes within a row only)
+          for (int e = 0; e < 8; ++e) t += scratch[tid * 8 + e];
+        }
+        a.bias_partial[(int64_t)ks * a.Cout + q0 + tid] = t;
+      }
     }
   }
   tc_fence_before();
@@ -259,8 +293,15 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 // out[co][ci][tap] = sum over ks of partial[ks][tap][ci][co], added in index order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_ks, int taps, int Cin, int Cout) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_ks, int taps, int Cin, int Cout,
+                                    const float* __restrict__ bias_partial, float* __restrict__ g_bias) {
   const int64_t n = (int64_t)taps * Cin * Cout;
+  if (g_bias != nullptr && blockIdx.x == 0)
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < n_ks; ++k) acc += bias_partial[(int64_t)k * Cout + co];
+      g_bias[co] = acc;
+    }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // i indexes [tap][ci][co] (coalesced reads); the write is the permuted position
     const int co = (int)(i % Cout);
@@ -289,11 +330,11 @@ using namespace mflow;
 extern "C" MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* d) {
   if (!d) return 0;
   const int64_t taps = d->kernel == 3 ? 9 : 1;
-  return (int64_t)wgrad_splits(d) * taps * d->c_in * d->c_out * (int64_t)sizeof(float);
+  return (int64_t)wgrad_splits(d) * (taps * d->c_in * d->c_out + d->c_out) * (int64_t)sizeof(float);
 }
 
 extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, const float* x, const float* g_y, float* g_w,
-                                                   void* workspace, void* stream) {
+                                                   float* g_bias, void* workspace, void* stream) {
   MFLOW_REQUIRE(d && x && g_y && g_w && workspace, "null pointer");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
   MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
@@ -320,6 +361,7 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   a.tmem_cols = 512;
   MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + 4 * kWgPCols <= 512, "accumulators do not fit in tensor memory");
   const int n_ks = wgrad_splits(d);
+  a.bias_partial = g_bias ? a.partial + (int64_t)n_ks * a.taps * a.Cin * a.Cout : nullptr;
 
   CUtensorMap mx, mg;
   {  // activations, NCHW: box {box_w, rows, 128 channels, 1 image}; lands as [channel][row][w]
@@ -357,6 +399,6 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   const int64_t n_out = (int64_t)a.taps * a.Cin * a.Cout;
   int rgrid = (int)((n_out + 255) / 256);
   if (rgrid > 4 * kNumSMs) rgrid = 4 * kNumSMs;
-  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(a.partial, g_w, n_ks, a.taps, a.Cin, a.Cout);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(a.partial, g_w, n_ks, a.taps, a.Cin, a.Cout, a.bias_partial, g_bias);
   return check_launch("wgrad_tf32x3_kernel");
 }

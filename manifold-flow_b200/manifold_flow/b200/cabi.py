@@ -65,7 +65,7 @@ _SIGNATURES = {
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
     "mflow_conv2d_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
     "mflow_conv2d_wgrad_workspace_bytes": (i64, [ctypes.POINTER(ConvDesc)]),
-    "mflow_conv2d_wgrad_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 5),
+    "mflow_conv2d_wgrad_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 6),
     "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),
     "mflow_chanmix_wgrad_workspace_bytes": (i64, [ctypes.POINTER(MixDesc)]),
     "mflow_chanmix_wgrad": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 6),

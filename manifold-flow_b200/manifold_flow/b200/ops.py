@@ -270,23 +270,25 @@ def conv_wgrad_supported(x, c_out, kernel):
     return h == w and w in (4, 8, 16, 32) and w >= config.conv_wgrad_min_width and b >= 1 and (kernel == 1 or c_out <= 112)
 
 
-def conv_wgrad_tc(g, x, kernel, relu_in):
-    """g_w[co, ci, ky, kx] of y = conv2d(relu?(x), W): pixels-as-K GEMM on the tensor cores (3xTF32), deterministic."""
+def conv_wgrad_tc(g, x, kernel, relu_in, with_bias=False):
+    """g_w[co, ci, ky, kx] of y = conv2d(relu?(x), W): pixels-as-K GEMM on the tensor cores (3xTF32), deterministic.
+    with_bias: also return the bias gradient sum_{b,h,w} g (computed inside the same kernel) as (g_w, g_b)."""
     require_cuda(g, x)
     g, x = _c(g), _c(x)
     b, c_in, h, w = x.shape
     c_out = g.shape[1]
     d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0, n_pad=0, k_pad=0)
     gw = torch.empty((c_out, c_in, kernel, kernel), dtype=torch.float32, device=x.device)
+    gb = torch.empty(c_out, dtype=torch.float32, device=x.device) if with_bias else None
     ws = cabi.workspace("conv_wgrad", lib().mflow_conv2d_wgrad_workspace_bytes(ctypes.byref(d)), x.device)
     tok = None
     if cabi.kernel_timer:
         tok = cabi.kernel_timer.begin(f"wgrad{kernel}x{kernel}[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out * kernel * kernel)
-    check(lib().mflow_conv2d_wgrad_tf32x3(ctypes.byref(d), ptr(x), ptr(g), ptr(gw), ptr(ws), stream()), "mflow_conv2d_wgrad_tf32x3")
+    check(lib().mflow_conv2d_wgrad_tf32x3(ctypes.byref(d), ptr(x), ptr(g), ptr(gw), ptr(gb), ptr(ws), stream()), "mflow_conv2d_wgrad_tf32x3")
     if tok:
         cabi.kernel_timer.end(tok)
     cabi.count_launch(2)
-    return gw
+    return (gw, gb) if with_bias else gw
 
 
 class _ConvTC(torch.autograd.Function):
@@ -314,13 +316,17 @@ class _ConvTC(torch.autograd.Function):
         kernel = weight.shape[2]
         if ctx.needs_input_grad[0]:
             gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner), weight.shape[1], kernel, None, None, x if ctx.relu_in else None, False)
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
-            gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in)
+            if want_bias:   # the weight-gradient kernel sums g over the pixels on the side
+                gw, gb = conv_wgrad_tc(g, x, kernel, ctx.relu_in, with_bias=True)
+            else:
+                gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in)
         elif ctx.needs_input_grad[1]:   # shapes the tensor-core kernel does not take (4x4 maps): library call
             xin = torch.relu(x) if ctx.relu_in else x
             gw = torch.ops.aten.convolution_backward(g, xin, weight, None, [1, 1], [kernel // 2] * 2, [1, 1], False, [0, 0], 1,
                                                      [False, True, False])[1]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if want_bias and gb is None:
             gb = channel_sum(g)
         return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None, None
 

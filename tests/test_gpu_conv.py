@@ -123,6 +123,12 @@ def test_wgrad_tensor_core_matches_fp64_autograd(cuda_device, case):
     rel = ((got.double() - w.grad).norm() / w.grad.norm()).item()
     assert rel < 2e-6, rel                                   # fp32 library wgrad sits at 1e-7 .. 2e-6 on these
     assert torch.equal(got, ops.conv_wgrad_tc(g, x, k, relu))   # deterministic
+    # the bias gradient rides along in the same kernel
+    got2, gb = ops.conv_wgrad_tc(g, x, k, relu, with_bias=True)
+    assert torch.equal(got, got2)
+    want_b = g.double().sum(dim=(0, 2, 3))
+    scale_b = g.double().abs().sum(dim=(0, 2, 3)).clamp_min(1.0)
+    assert ((gb.double() - want_b).abs() / scale_b).max().item() < 1e-6
 
 
 @pytest.mark.gpu
