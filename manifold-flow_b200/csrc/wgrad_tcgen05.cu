@@ -292,24 +292,42 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem, a.tmem_cols);
 }
 
-// out[co][ci][tap] = sum over ks of partial[ks][tap][ci][co], added in index order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_ks, int taps, int Cin, int Cout,
-                                    const float* __restrict__ bias_partial, float* __restrict__ g_bias) {
+// out[co][ci][tap] = sum over ks of partial[ks][tap][ci][co].
+// block = 32 outputs x 8 k-lanes: lane q of an output adds the splits q, q + 8, ... (short dependent chains, 128-byte
+// coalesced reads for a fixed split), then the 8 lane sums are combined in a fixed shuffle tree: deterministic.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_ks, int taps,
+                                                           int Cin, int Cout, const float* __restrict__ bias_partial,
+                                                           float* __restrict__ g_bias) {
   const int64_t n = (int64_t)taps * Cin * Cout;
-  if (g_bias != nullptr && blockIdx.x == 0)
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-      float acc = 0.f;
-      for (int k = 0; k < n_ks; ++k) acc += bias_partial[(int64_t)k * Cout + co];
-      g_bias[co] = acc;
-    }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    // i indexes [tap][ci][co] (coalesced reads); the write is the permuted position
-    const int co = (int)(i % Cout);
-    const int ci = (int)((i / Cout) % Cin);
-    const int tap = (int)(i / ((int64_t)Cout * Cin));
+  const int o_in_blk = threadIdx.x & 31, q = threadIdx.x >> 5;   // warp w = k-lane w: its 32 lanes are 32 consecutive outputs
+  __shared__ float s_part[8][33];
+  const int64_t n_items = n + (g_bias != nullptr ? Cout : 0);    // the bias gradient's Cout sums are appended to the work list
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < n_items; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + o_in_blk;
     float acc = 0.f;
-    for (int k = 0; k < n_ks; ++k) acc += partial[(int64_t)k * n + i];
-    out[((int64_t)co * Cin + ci) * taps + tap] = acc;
+    if (i < n) {
+      for (int k = q; k < n_ks; k += 8) acc += partial[(int64_t)k * n + i];
+    } else if (i < n_items) {
+      const int co = (int)(i - n);
+      for (int k = q; k < n_ks; k += 8) acc += bias_partial[(int64_t)k * Cout + co];
+    }
+    s_part[q][o_in_blk] = acc;
+    __syncthreads();
+    if (q == 0 && i < n_items) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += s_part[r][o_in_blk];
+      if (i < n) {
+        // i indexes [tap][ci][co] (coalesced reads); the write is the permuted position
+        const int co = (int)(i % Cout);
+        const int ci = (int)((i / Cout) % Cin);
+        const int tap = (int)(i / ((int64_t)Cout * Cin));
+        out[((int64_t)co * Cin + ci) * taps + tap] = t;
+      } else {
+        g_bias[i - n] = t;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -397,8 +415,8 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   }
 #undef MFLOW_WGRAD_LAUNCH
   const int64_t n_out = (int64_t)a.taps * a.Cin * a.Cout;
-  int rgrid = (int)((n_out + 255) / 256);
-  if (rgrid > 4 * kNumSMs) rgrid = 4 * kNumSMs;
+  int64_t rblocks = (n_out + a.Cout + 31) / 32;
+  const int rgrid = (int)(rblocks > 16 * kNumSMs ? 16 * kNumSMs : rblocks);
   wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(a.partial, g_w, n_ks, a.taps, a.Cin, a.Cout, a.bias_partial, g_bias);
   return check_launch("wgrad_tf32x3_kernel");
 }
