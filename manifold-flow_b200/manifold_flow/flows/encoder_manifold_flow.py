@@ -18,7 +18,7 @@ class EncoderManifoldFlow(ManifoldFlow):
     def forward(self, x, mode="mf", context=None, return_hidden=False):
         if mode not in ("mf", "projection", "pie", "mf-fixed-manifold"):
             raise ValueError("unsupported mode {!r}".format(mode))
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         u, h_manifold, log_det_inner = self._encode(x, context)
         x_reco, inv_log_det_inner, inv_log_det_outer, inv_jacobian_outer, _ = self._decode(u, mode=mode, context=context)
         if mode == "mf":
@@ -32,7 +32,7 @@ class EncoderManifoldFlow(ManifoldFlow):
         return x_reco, log_prob, u
 
     def encode(self, x, context=None):
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         return self._encode(x, context)[0]
 
     def _encode(self, x, context=None):

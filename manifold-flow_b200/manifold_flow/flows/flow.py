@@ -24,14 +24,14 @@ class Flow(BaseFlow):
         """(x_reco, log_prob, u) - flow.py:26-39.  The reconstruction only feeds diagnostics in the
         reference's trainers (the NLL loss does not depend on it), so it is computed without
         recording an autograd graph."""
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         u, log_det = self._encode(x, context=context)
         with torch.no_grad():
             x_reco = self.decode(u.detach(), context=context)
         return x_reco, self._density(u, log_det), u
 
     def encode(self, x, context=None):
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         return self._encode(x, context=context)[0]
 
     def decode(self, u, context=None):
@@ -39,7 +39,7 @@ class Flow(BaseFlow):
 
     def log_prob(self, x, context=None):
         """flow.py:53-63"""
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         u, log_det = self._encode(x, context)
         return self._density(u, log_det)
 

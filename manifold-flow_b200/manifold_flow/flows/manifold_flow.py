@@ -48,7 +48,7 @@ class ManifoldFlow(BaseFlow):
         "pie-inv" raises TypeError in the reference and is not offered."""
         if mode not in _MODES:
             raise ValueError("mode must be one of {}, got {!r}".format(_MODES, mode))
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         u, h_manifold, h_orthogonal, log_det_outer, log_det_inner = self._encode(x, context)
         x_reco, inv_log_det_inner, inv_log_det_outer, inv_jacobian_outer, _ = self._decode(u, mode=mode, context=context)
         log_prob = self._log_prob(mode, u, h_orthogonal, log_det_inner, log_det_outer, inv_log_det_inner, inv_log_det_outer, inv_jacobian_outer)
@@ -57,7 +57,7 @@ class ManifoldFlow(BaseFlow):
         return x_reco, log_prob, u
 
     def encode(self, x, context=None):
-        fusion.begin_pass()
+        fusion.begin_pass(self)
         return self._encode(x, context=context)[0]
 
     def decode(self, u, u_orthogonal=None, context=None):

@@ -18,11 +18,17 @@ MAX_FUSED_CHANNELS = 96  # chanmix weight-gradient kernel limit (shared memory)
 _pass_id = 0
 
 
-def begin_pass():
+def begin_pass(model=None):
     """Called at the start of every model-level forward: dense L/U and composed matrices built
-    under autograd are reused by all transforms evaluated within the same pass."""
+    under autograd are reused by all transforms evaluated within the same pass.  The first pass of a
+    model also groups its LU layers for batched matrix builds (``lu.LUGroup``)."""
     global _pass_id
     _pass_id += 1
+    if model is not None and config.batch_lu_builds and not model.__dict__.get("_lu_groups_ready", False):
+        from .lu import assign_lu_groups
+
+        assign_lu_groups(model)
+        model.__dict__["_lu_groups_ready"] = True
     return _pass_id
 
 

@@ -25,3 +25,46 @@ def test_blocked_trisolve_math(n, m, block):
     junk = lower.clone()
     junk.diagonal().fill_(7.0)
     assert torch.allclose(_blocked_trisolve(junk, rhs, False, True, block), _blocked_trisolve(lower, rhs, False, True, block), atol=1e-12)
+
+
+def test_lu_group_matches_per_layer_builds():
+    """lu.LUGroup (batched dense L / U / W / W^-1 / logabsdet of same-width LU layers, reference lu.py:44-128 per layer)
+    reproduces the per-layer construction, values and parameter gradients."""
+    import copy
+
+    from torch import nn
+
+    from manifold_flow import transforms
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(5)
+    layers = nn.ModuleList([transforms.OneByOneConvolution(12) for _ in range(4)] + [transforms.LULinear(12) for _ in range(3)]
+                           + [transforms.OneByOneConvolution(24)])
+    for p in layers.parameters():
+        p.data.normal_(0.0, 0.3)
+    grouped = copy.deepcopy(layers)
+    assign_lu_groups(grouped)
+    assert all(getattr(m, "_lu_group", None) is not None for m in list(grouped)[:7])
+    assert getattr(grouped[7], "_lu_group", None) is None          # a single layer of its width stays on its own
+    assert grouped[0]._lu_group is not grouped[4]._lu_group        # different classes are not mixed
+
+    def scalar(ms):
+        total = 0.0
+        for i, m in enumerate(ms):
+            w, wi, lad = m.weight(), m.weight_inverse(), m.logabsdet()
+            total = total + (w * (i + 1)).sin().sum() + (wi * 0.5).cos().sum() + lad * (i + 2)
+        return total
+
+    ref, got = scalar(layers), scalar(grouped)
+    assert torch.allclose(ref, got, rtol=1e-5, atol=1e-5)
+    for a, b in zip(layers, grouped):
+        assert torch.allclose(a.weight(), b.weight(), atol=1e-6)
+        assert torch.allclose(a.weight_inverse(), b.weight_inverse(), atol=1e-5)
+        assert torch.allclose(a.logabsdet(), b.logabsdet(), atol=1e-6)
+    ref.backward()
+    got.backward()
+    for (n, pa), (_, pb) in zip(layers.named_parameters(), grouped.named_parameters()):
+        if pa.grad is None:
+            assert pb.grad is None, n
+        else:
+            assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
