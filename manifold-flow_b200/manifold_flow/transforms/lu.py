@@ -118,6 +118,11 @@ class LULinear(Linear):
         return self.features <= MAX_FUSED_CHANNELS and x.dim() == 2
 
     def _affine_map(self, inverse):
+        group = getattr(self, "_lu_group", None)
+        if group is not None:
+            mat, bias, lad = group.affine_maps(inverse)
+            return mat[self._lu_index], bias[self._lu_index], lad[self._lu_index]
+
         def build():
             if not inverse:
                 return self.weight(), self.bias, self.logabsdet()
@@ -170,6 +175,8 @@ class LUGroup:
         self._factors = VersionedCache()
         self._products = VersionedCache()
         self._inverses = VersionedCache()
+        self._maps = {False: VersionedCache(), True: VersionedCache()}
+        self._inv_perm = None
 
     def _params(self):
         return tuple(p for layer in self.layers for p in layer._lu_params())
@@ -206,6 +213,37 @@ class LUGroup:
 
         return self._inverses.get(self._params(), build)
 
+    def _inverse_permutations(self):
+        """[G, n] inverse channel permutations of the members (1x1 convolutions), or None for plain LULinear."""
+        first = self.layers[0]
+        if getattr(first, "permutation", None) is None:
+            return None
+        device = first.lower_entries.device
+        if self._inv_perm is None or self._inv_perm.device != device:
+            self._inv_perm = torch.stack([layer.permutation._inverse_permutation for layer in self.layers]).to(device)
+        return self._inv_perm
+
+    def affine_maps(self, inverse):
+        """Stacked per-pixel affine maps (M [G,n,n], m [G,n], logabsdet [G]) of the members: y = W x[perm] + b forward
+        (conv.py:33-41; no permutation for LULinear, lu.py:56-73) or x = (W^-1 (y - b))[inv_perm] (conv.py:43-55)."""
+
+        def build():
+            bias = torch.stack([layer.bias for layer in self.layers])
+            lad = self.factors()[2]
+            inv_perm = self._inverse_permutations()
+            g, n = bias.shape
+            if not inverse:
+                mat = self.products()
+                if inv_perm is not None:
+                    mat = torch.gather(mat, 2, inv_perm[:, None, :].expand(g, n, n))      # W[:, inv_perm]
+                return mat, bias, lad
+            mat = self.inverses()
+            if inv_perm is not None:
+                mat = torch.gather(mat, 1, inv_perm[:, :, None].expand(g, n, n))          # W^-1[inv_perm, :]
+            return mat, -torch.bmm(mat, bias[:, :, None]).squeeze(2), -lad
+
+        return self._maps[bool(inverse)].get(self._params() + tuple(layer.bias for layer in self.layers), build)
+
 
 def assign_lu_groups(model):
     """Group the fusable LU layers of ``model`` (same class, width, eps, device) so that their dense matrices are
@@ -222,3 +260,17 @@ def assign_lu_groups(model):
         for index, layer in enumerate(layers):
             object.__setattr__(layer, "_lu_group", group)
             object.__setattr__(layer, "_lu_index", index)
+    from .normalization import ActNorm, ActNormGroup
+
+    buckets = {}
+    for module in model.modules():
+        if isinstance(module, ActNorm) and module.log_scale.numel() <= MAX_FUSED_CHANNELS:
+            key = (module.log_scale.numel(), str(module.log_scale.device), module.log_scale.dtype)
+            buckets.setdefault(key, []).append(module)
+    for layers in buckets.values():
+        if len(layers) < 2:
+            continue
+        group = ActNormGroup(layers)
+        for index, layer in enumerate(layers):
+            object.__setattr__(layer, "_an_group", group)
+            object.__setattr__(layer, "_an_index", index)

@@ -31,6 +31,10 @@ class ActNorm(Transform):
         return self.training and not self.initialized
 
     def _affine_map(self, inverse):
+        group = getattr(self, "_an_group", None)
+        if group is not None and group.ready():
+            mat, bias, lad = group.affine_maps(inverse)
+            return mat[self._an_index], bias[self._an_index], lad[self._an_index]
         if not inverse:  # :99-116
             return torch.diag(self.scale), self.shift, torch.sum(self.log_scale)
         inv_scale = torch.exp(-self.log_scale)  # :118-131
@@ -62,6 +66,33 @@ class ActNorm(Transform):
             self.log_scale.data.copy_(log_scale)
             self.shift.data.copy_(shift)
         self.initialized = True
+
+
+class ActNormGroup:
+    """Stacked affine maps of all same-width ActNorm layers of a model (one exp / diag_embed / sum instead of one
+    per layer).  Used only once every member has had its data-dependent initialisation (which writes the
+    parameters behind autograd's back, so a cache built earlier could go stale)."""
+
+    def __init__(self, layers):
+        from .fusion import VersionedCache
+
+        self.layers = list(layers)
+        self._maps = {False: VersionedCache(), True: VersionedCache()}
+
+    def ready(self):
+        return all(layer.initialized or not layer.training for layer in self.layers)
+
+    def affine_maps(self, inverse):
+        def build():
+            log_scale = torch.stack([layer.log_scale for layer in self.layers])
+            shift = torch.stack([layer.shift for layer in self.layers])
+            if not inverse:
+                return torch.diag_embed(torch.exp(log_scale)), shift, log_scale.sum(dim=1)
+            inv_scale = torch.exp(-log_scale)
+            return torch.diag_embed(inv_scale), -shift * inv_scale, -log_scale.sum(dim=1)
+
+        params = tuple(p for layer in self.layers for p in (layer.log_scale, layer.shift))
+        return self._maps[bool(inverse)].get(params, build)
 
 
 class BatchNorm:

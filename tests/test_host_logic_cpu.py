@@ -55,6 +55,9 @@ def test_lu_group_matches_per_layer_builds():
             total = total + (w * (i + 1)).sin().sum() + (wi * 0.5).cos().sum() + lad * (i + 2)
         return total
 
+    from manifold_flow.transforms import fusion
+
+    fusion.begin_pass()
     ref, got = scalar(layers), scalar(grouped)
     assert torch.allclose(ref, got, rtol=1e-5, atol=1e-5)
     for a, b in zip(layers, grouped):
@@ -68,3 +71,51 @@ def test_lu_group_matches_per_layer_builds():
             assert pb.grad is None, n
         else:
             assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
+
+
+def test_grouped_affine_maps_match_per_layer_maps():
+    """The stacked (M, m, logabsdet) maps of lu.LUGroup / normalization.ActNormGroup equal the per-layer
+    `_affine_map` results (conv.py:33-55, lu.py:56-95, normalization.py:99-131), values and gradients, both directions."""
+    import copy
+
+    from torch import nn
+
+    from manifold_flow import transforms
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(9)
+    layers = nn.ModuleList([transforms.OneByOneConvolution(12) for _ in range(3)] + [transforms.LULinear(12) for _ in range(2)]
+                           + [transforms.ActNorm(12) for _ in range(3)])
+    for p in layers.parameters():
+        p.data.normal_(0.0, 0.3)
+    for m in layers:
+        if isinstance(m, transforms.ActNorm):
+            m.initialized = True
+    grouped = copy.deepcopy(layers)
+    assign_lu_groups(grouped)
+    assert all(getattr(m, "_lu_group", None) is not None for m in list(grouped)[:5])
+    assert all(getattr(m, "_an_group", None) is not None for m in list(grouped)[5:])
+    from manifold_flow.transforms import fusion
+
+    for inverse in (False, True):
+        fusion.begin_pass()   # a model-level forward starts a new pass: graphs cached in the previous one are not reused
+        for ms in (layers, grouped):
+            for p in ms.parameters():
+                p.grad = None
+        totals = []
+        for ms in (layers, grouped):
+            total = 0.0
+            for i, m in enumerate(ms):
+                mat, bias, lad = m._affine_map(inverse)
+                total = total + (mat * (i + 1)).sin().sum() + (bias * 0.7).cos().sum() + lad * (i + 2)
+            totals.append(total)
+        assert torch.allclose(totals[0], totals[1], rtol=1e-5, atol=1e-5)
+        for a, b in zip(layers, grouped):
+            for x, y in zip(a._affine_map(inverse), b._affine_map(inverse)):
+                assert torch.allclose(x, y, atol=1e-5)
+        totals[0].backward()
+        totals[1].backward()
+        for (n, pa), (_, pb) in zip(layers.named_parameters(), grouped.named_parameters()):
+            assert (pa.grad is None) == (pb.grad is None), n
+            if pa.grad is not None:
+                assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
