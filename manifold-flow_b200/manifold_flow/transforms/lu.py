@@ -274,3 +274,26 @@ def assign_lu_groups(model):
         for index, layer in enumerate(layers):
             object.__setattr__(layer, "_an_group", group)
             object.__setattr__(layer, "_an_index", index)
+    # adjacent (ActNorm, 1x1 convolution) members of a chain, both grouped: compose all such pairs of a width together
+    from .base import CompositeTransform
+    from .conv import OneByOneConvolution
+    from .fusion import PairGroup
+
+    pair_buckets = {}
+    for module in model.modules():
+        if not isinstance(module, CompositeTransform):
+            continue
+        chain = list(module._transforms)
+        for first, second in zip(chain[:-1], chain[1:]):
+            if (isinstance(first, ActNorm) and isinstance(second, OneByOneConvolution) and getattr(first, "_an_group", None) is not None
+                    and getattr(second, "_lu_group", None) is not None and first.log_scale.numel() == second.features
+                    and getattr(first, "_pair_group", None) is None):
+                pair_buckets.setdefault((first._an_group, second._lu_group), []).append((first, second))
+    for pairs in pair_buckets.values():
+        if len(pairs) < 2:
+            continue
+        group = PairGroup(pairs)
+        for index, (act, conv) in enumerate(pairs):
+            object.__setattr__(act, "_pair_group", group)
+            object.__setattr__(act, "_pair_index", index)
+            object.__setattr__(act, "_pair_partner", conv)

@@ -119,3 +119,54 @@ def test_grouped_affine_maps_match_per_layer_maps():
             assert (pa.grad is None) == (pb.grad is None), n
             if pa.grad is not None:
                 assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
+
+
+def test_pair_group_composition_matches_sequential_composition():
+    """fusion.PairGroup: conv(actnorm(x)) and its inverse composed for all pairs at once equal the per-pair
+    composition of fusion.apply_affine (values and gradients)."""
+    import copy
+
+    from torch import nn
+
+    from manifold_flow import transforms
+    from manifold_flow.transforms import fusion
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(21)
+    steps = [transforms.CompositeTransform([transforms.ActNorm(12), transforms.OneByOneConvolution(12)]) for _ in range(3)]
+    model = nn.ModuleList(steps)
+    for p in model.parameters():
+        p.data.normal_(0.0, 0.3)
+    for m in model.modules():
+        if isinstance(m, transforms.ActNorm):
+            m.initialized = True
+    grouped = copy.deepcopy(model)
+    assign_lu_groups(grouped)
+    assert all(getattr(s._transforms[0], "_pair_group", None) is not None for s in grouped)
+
+    def compose(maps):
+        mat, bias, lad = maps[0]
+        for m2, b2, l2 in maps[1:]:
+            bias, mat, lad = m2 @ bias + b2, m2 @ mat, lad + l2
+        return mat, bias, lad
+
+    for inverse in (False, True):
+        fusion.begin_pass()
+        ref_total, got_total = 0.0, 0.0
+        for i, (ref_step, got_step) in enumerate(zip(model, grouped)):
+            order = [1, 0] if inverse else [0, 1]
+            ref = compose([ref_step._transforms[j]._affine_map(inverse) for j in order])
+            act = got_step._transforms[0]
+            stacked = act._pair_group.composed(inverse)
+            got = tuple(t[act._pair_index] for t in stacked)
+            for a, b in zip(ref, got):
+                assert torch.allclose(a, b, atol=1e-5)
+            ref_total = ref_total + (ref[0] * (i + 1)).sin().sum() + ref[1].cos().sum() + ref[2]
+            got_total = got_total + (got[0] * (i + 1)).sin().sum() + got[1].cos().sum() + got[2]
+        for ms in (model, grouped):
+            for p in ms.parameters():
+                p.grad = None
+        ref_total.backward()
+        got_total.backward()
+        for (n, pa), (_, pb) in zip(model.named_parameters(), grouped.named_parameters()):
+            assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
