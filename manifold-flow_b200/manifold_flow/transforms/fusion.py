@@ -116,31 +116,48 @@ class VersionedCache:
 
 
 class PairGroup:
-    """Composed maps of all (ActNorm -> 1x1 convolution) pairs of one width: conv(actnorm(x)) forward,
-    actnorm^-1(conv^-1(y)) inverse, as three batched products instead of four small launches per pair."""
+    """Composed maps of all (ActNorm -> 1x1 convolution) pairs - or (RandomPermutation -> LULinear) pairs of the
+    vector flows - of one width: second(first(x)) forward, first^-1(second^-1(y)) inverse, as a few batched products
+    instead of four small launches per pair."""
 
-    def __init__(self, pairs):
-        self.pairs = list(pairs)   # [(ActNorm, OneByOneConvolution)]
+    def __init__(self, pairs, kind):
+        self.pairs = list(pairs)   # [(first, second)]
+        self.kind = kind           # "actnorm" | "perm"
         self._composed = {False: VersionedCache(), True: VersionedCache()}
         self._idx = None
+        self._perm_mats = {}
 
     def ready(self):
-        return self.pairs[0][0]._an_group.ready()
+        return self.kind == "perm" or self.pairs[0][0]._an_group.ready()
+
+    def _first_maps(self, inverse, device):
+        if self.kind == "actnorm":
+            return tuple(t.index_select(0, self._idx[0]) for t in self.pairs[0][0]._an_group.affine_maps(inverse))
+        key = (bool(inverse), str(device))
+        if key not in self._perm_mats:   # constant: the permutation buffers never change
+            n = self.pairs[0][0]._permutation.numel()
+            eye = torch.eye(n, dtype=torch.float32, device=device)
+            self._perm_mats[key] = torch.stack([eye[(p._inverse_permutation if inverse else p._permutation).to(device), :]
+                                                for p, _ in self.pairs])
+        return self._perm_mats[key], None, None
 
     def composed(self, inverse):
-        act0, conv0 = self.pairs[0]
+        first0, second0 = self.pairs[0]
 
         def build():
-            device = act0.log_scale.device
-            if self._idx is None or self._idx[0].device != device:
-                self._idx = (torch.tensor([a._an_index for a, _ in self.pairs], device=device),
-                             torch.tensor([c._lu_index for _, c in self.pairs], device=device))
-            ia, ic = self._idx
-            ma, ba, la = (t.index_select(0, ia) for t in act0._an_group.affine_maps(inverse))
-            mc, bc, lc = (t.index_select(0, ic) for t in conv0._lu_group.affine_maps(inverse))
-            if not inverse:   # x -> actnorm -> conv
-                return torch.bmm(mc, ma), torch.bmm(mc, ba[:, :, None]).squeeze(2) + bc, la + lc
-            return torch.bmm(ma, mc), torch.bmm(ma, bc[:, :, None]).squeeze(2) + ba, la + lc   # y -> conv^-1 -> actnorm^-1
+            device = second0.lower_entries.device
+            if self._idx is None or self._idx[1].device != device:
+                ia = torch.tensor([a._an_index for a, _ in self.pairs], device=device) if self.kind == "actnorm" else None
+                self._idx = (ia, torch.tensor([c._lu_index for _, c in self.pairs], device=device))
+            ma, ba, la = self._first_maps(inverse, device)
+            mc, bc, lc = (t.index_select(0, self._idx[1]) for t in second0._lu_group.affine_maps(inverse))
+            if not inverse:   # x -> first -> second
+                bias = bc if ba is None else torch.bmm(mc, ba[:, :, None]).squeeze(2) + bc
+                return torch.bmm(mc, ma), bias, (lc if la is None else la + lc)
+            bias = torch.bmm(ma, bc[:, :, None]).squeeze(2)   # y -> second^-1 -> first^-1
+            return torch.bmm(ma, mc), (bias if ba is None else bias + ba), (lc if la is None else la + lc)
 
-        params = tuple(p for a, c in self.pairs for p in (a.log_scale, a.shift, c.bias) + c._lu_params())
+        params = tuple(p for _, c in self.pairs for p in (c.bias,) + c._lu_params())
+        if self.kind == "actnorm":
+            params = params + tuple(p for a, _ in self.pairs for p in (a.log_scale, a.shift))
         return self._composed[bool(inverse)].get(params, build)

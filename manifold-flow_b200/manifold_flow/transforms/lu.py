@@ -279,21 +279,27 @@ def assign_lu_groups(model):
     from .conv import OneByOneConvolution
     from .fusion import PairGroup
 
+    from .permutations import Permutation
+
     pair_buckets = {}
     for module in model.modules():
         if not isinstance(module, CompositeTransform):
             continue
         chain = list(module._transforms)
         for first, second in zip(chain[:-1], chain[1:]):
+            if getattr(second, "_lu_group", None) is None or getattr(first, "_pair_group", None) is not None:
+                continue
             if (isinstance(first, ActNorm) and isinstance(second, OneByOneConvolution) and getattr(first, "_an_group", None) is not None
-                    and getattr(second, "_lu_group", None) is not None and first.log_scale.numel() == second.features
-                    and getattr(first, "_pair_group", None) is None):
-                pair_buckets.setdefault((first._an_group, second._lu_group), []).append((first, second))
-    for pairs in pair_buckets.values():
+                    and first.log_scale.numel() == second.features):
+                pair_buckets.setdefault(("actnorm", first._an_group, second._lu_group), []).append((first, second))
+            elif (isinstance(first, Permutation) and type(second) is LULinear and first._dim == 1
+                  and first._permutation.numel() == second.features):
+                pair_buckets.setdefault(("perm", None, second._lu_group), []).append((first, second))
+    for (kind, _, _), pairs in pair_buckets.items():
         if len(pairs) < 2:
             continue
-        group = PairGroup(pairs)
-        for index, (act, conv) in enumerate(pairs):
-            object.__setattr__(act, "_pair_group", group)
-            object.__setattr__(act, "_pair_index", index)
-            object.__setattr__(act, "_pair_partner", conv)
+        group = PairGroup(pairs, kind)
+        for index, (first, second) in enumerate(pairs):
+            object.__setattr__(first, "_pair_group", group)
+            object.__setattr__(first, "_pair_index", index)
+            object.__setattr__(first, "_pair_partner", second)

@@ -170,3 +170,45 @@ def test_pair_group_composition_matches_sequential_composition():
         got_total.backward()
         for (n, pa), (_, pb) in zip(model.named_parameters(), grouped.named_parameters()):
             assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
+
+
+def test_pair_group_permutation_lu_pairs():
+    """(RandomPermutation -> LULinear) glue of the vector flows (vector_transforms.py:139-177): PairGroup composition
+    equals the sequential composition, both directions, values and gradients."""
+    import copy
+
+    from torch import nn
+
+    from manifold_flow import transforms
+    from manifold_flow.transforms import fusion
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(23)
+    steps = [transforms.CompositeTransform([transforms.RandomPermutation(features=14), transforms.LULinear(14)]) for _ in range(4)]
+    model = nn.ModuleList(steps)
+    for p in model.parameters():
+        p.data.normal_(0.0, 0.3)
+    grouped = copy.deepcopy(model)
+    assign_lu_groups(grouped)
+    assert all(getattr(s._transforms[0], "_pair_group", None) is not None for s in grouped)
+    for inverse in (False, True):
+        fusion.begin_pass()
+        ref_total, got_total = 0.0, 0.0
+        for i, (ref_step, got_step) in enumerate(zip(model, grouped)):
+            order = [1, 0] if inverse else [0, 1]
+            maps = [ref_step._transforms[j]._affine_map(inverse) for j in order]
+            mat, bias, lad = maps[0]
+            mat, bias, lad = maps[1][0] @ mat, maps[1][0] @ bias + maps[1][1], lad + maps[1][2]
+            first = got_step._transforms[0]
+            got = tuple(t[first._pair_index] for t in first._pair_group.composed(inverse))
+            for a, b in zip((mat, bias, lad), got):
+                assert torch.allclose(a, b, atol=1e-5)
+            ref_total = ref_total + (mat * (i + 1)).sin().sum() + bias.cos().sum() + lad
+            got_total = got_total + (got[0] * (i + 1)).sin().sum() + got[1].cos().sum() + got[2]
+        for ms in (model, grouped):
+            for p in ms.parameters():
+                p.grad = None
+        ref_total.backward()
+        got_total.backward()
+        for (n, pa), (_, pb) in zip(model.named_parameters(), grouped.named_parameters()):
+            assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
