@@ -71,7 +71,7 @@ typedef struct {
   int64_t x_so, x_sc;
   int64_t y_so, y_sc;
   int64_t p_so, p_sc, p_sp, p_si;
-  int32_t num_bins; /* K in {2..16} */
+  int32_t num_bins; /* K in {2..16, 20, 24, 32} */
   int32_t inverse;  /* 0 forward, 1 inverse */
   float tail_bound; /* T: spline on [-T, T]^2, identity outside (closed interval) */
   float min_bin_width, min_bin_height, min_derivative;
@@ -103,6 +103,27 @@ MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* desc, const float* x, const 
 MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* desc, const float* x_in, const float* x_out,
                        const float* params, const float* g_out, const float* g_lad_sample,
                        const float* g_lad_elem, float* g_in, float* g_params, void* stream);
+
+/* Spline on a box: rational_quadratic_spline(inputs, W, H, D, inverse, left, right, bottom, top, ...)
+ * of manifold_flow/transforms/splines/rational_quadratic.py:67-168 - the bounded spline the unconstrained
+ * wrapper calls, as a function of its own: all K+1 knot derivatives are parameters (no padding constant),
+ * the x knots span [left, right] and the y knots [bottom, top].
+ *   params : [n, 3K+1] rows = [K widths | K heights | K+1 derivatives] (unnormalised)
+ *   x, y, lad (per-element logabsdet) : [n];  bins : optional int32 [n]
+ * The caller checks the domain (the reference raises InputOutsideDomain, :85-86); an element outside the
+ * searched axis' range passes through unchanged with logabsdet 0 and bin -1. */
+typedef struct {
+  int64_t n;
+  int32_t num_bins;
+  int32_t inverse;
+  float left, right, bottom, top;
+  float min_bin_width, min_bin_height, min_derivative;
+} mflow_rqs_box_desc;
+MFLOW_API int mflow_rqs_box_apply(const mflow_rqs_box_desc* desc, const float* x, const float* params, float* y,
+                        float* lad, int32_t* bins, void* stream);
+MFLOW_API int mflow_rqs_box_backward(const mflow_rqs_box_desc* desc, const float* x_in, const float* x_out,
+                           const float* params, const float* g_out, const float* g_lad, float* g_in,
+                           float* g_params, void* stream);
 
 /* Test entry: the kernel's own bin search on caller-provided knots (bit-exactness pin,
  * utils/various.py:472-474).  knots [n, K+1] row-major, values [n] -> bins int32 [n]. */

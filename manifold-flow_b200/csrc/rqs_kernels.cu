@@ -241,6 +241,50 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// spline on a box [left, right] x [bottom, top] with all K+1 knot derivatives given
+// (rational_quadratic_spline, rational_quadratic.py:67-168): function-level API, one thread per element,
+// parameter rows [n, 3K+1] = [widths | heights | derivatives].
+// ---------------------------------------------------------------------------------------------
+struct RqsBoxArgs {
+  const float* x;
+  const float* x_out;
+  const float* params;
+  float* y;
+  float* lad;
+  int32_t* bins;
+  const float* g_out;
+  const float* g_lad;
+  float* g_params;
+  int64_t n;
+  RqsConsts c;
+};
+
+template <int K, bool INV, bool BWD>
+__global__ void __launch_bounds__(128) rqs_box_kernel(const RqsBoxArgs a) {
+  constexpr int NP = 3 * K + 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  float p[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) p[j] = a.params[i * NP + j];
+  const float v = a.x[i];
+  if (!BWD) {
+    float out, lad;
+    int bin;
+    rqs_eval<K, INV, NP>(v, p, a.c, out, lad, bin);
+    a.y[i] = out;
+    a.lad[i] = lad;
+    if (a.bins) a.bins[i] = bin;
+  } else {
+    float g_in;
+    float* gp = a.g_params + i * NP;
+    rqs_grad<K, INV, NP>(v, INV ? a.x_out[i] : 0.f, p, a.c, a.g_out ? a.g_out[i] : 0.f, a.g_lad ? a.g_lad[i] : 0.f, g_in,
+                         [&](int j, float val) { gp[j] = val; });
+    a.y[i] = g_in;
+  }
+}
+
 template <int K>
 __global__ void rqs_search_kernel(const float* knots, const float* values, int32_t* bins, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,18 +364,18 @@ static bool rows_fast_path(const mflow_rqs_desc* d) {
          d->n_id_chan <= 4 * kRowThreads;
 }
 
+// --splinebins is a free integer in the reference (experiments/train.py:60); every K from 2 to 16 plus 20, 24 and
+// 32 is compiled in (the parameters of an element live in registers, so K is a template argument)
+#define MFLOW_K_CASE(N_, ...) case N_: { constexpr int K = N_; __VA_ARGS__; break; }
 #define MFLOW_DISPATCH_K(K_, ...)                    \
   switch (K_) {                                      \
-    case 4: { constexpr int K = 4; __VA_ARGS__; break; }   \
-    case 5: { constexpr int K = 5; __VA_ARGS__; break; }   \
-    case 6: { constexpr int K = 6; __VA_ARGS__; break; }   \
-    case 8: { constexpr int K = 8; __VA_ARGS__; break; }   \
-    case 10: { constexpr int K = 10; __VA_ARGS__; break; } \
-    case 11: { constexpr int K = 11; __VA_ARGS__; break; } \
-    case 12: { constexpr int K = 12; __VA_ARGS__; break; } \
-    case 16: { constexpr int K = 16; __VA_ARGS__; break; } \
+    MFLOW_K_CASE(2, __VA_ARGS__) MFLOW_K_CASE(3, __VA_ARGS__) MFLOW_K_CASE(4, __VA_ARGS__) MFLOW_K_CASE(5, __VA_ARGS__)     \
+    MFLOW_K_CASE(6, __VA_ARGS__) MFLOW_K_CASE(7, __VA_ARGS__) MFLOW_K_CASE(8, __VA_ARGS__) MFLOW_K_CASE(9, __VA_ARGS__)     \
+    MFLOW_K_CASE(10, __VA_ARGS__) MFLOW_K_CASE(11, __VA_ARGS__) MFLOW_K_CASE(12, __VA_ARGS__) MFLOW_K_CASE(13, __VA_ARGS__) \
+    MFLOW_K_CASE(14, __VA_ARGS__) MFLOW_K_CASE(15, __VA_ARGS__) MFLOW_K_CASE(16, __VA_ARGS__) MFLOW_K_CASE(20, __VA_ARGS__) \
+    MFLOW_K_CASE(24, __VA_ARGS__) MFLOW_K_CASE(32, __VA_ARGS__)                                                             \
     default:                                         \
-      set_error("num_bins=%d is not compiled in (supported: 4,5,6,8,10,11,12,16)", (int)(K_)); \
+      set_error("num_bins=%d is not compiled in (supported: 2..16, 20, 24, 32)", (int)(K_)); \
       return MFLOW_E_BADARG;                         \
   }
 
@@ -445,4 +489,53 @@ extern "C" MFLOW_API int mflow_rqs_search(const float* knots, const float* value
   const unsigned grid = (unsigned)((n + 127) / 128);
   MFLOW_DISPATCH_K(num_bins, rqs_search_kernel<K><<<grid, 128, 0, (cudaStream_t)stream>>>(knots, values, bins, n));
   return check_launch("rqs_search_kernel");
+}
+
+// rational_quadratic_spline on a box (rational_quadratic.py:67-168); see include/mflow_b200.h
+static int fill_box(const mflow_rqs_box_desc* d, RqsBoxArgs& a) {
+  MFLOW_REQUIRE(d != nullptr, "null descriptor");
+  MFLOW_REQUIRE(d->n >= 0, "bad extents");
+  MFLOW_REQUIRE(d->right > d->left && d->top > d->bottom, "empty box");
+  MFLOW_REQUIRE((double)d->min_bin_width * d->num_bins <= 1.0, "Minimal bin width too large for the number of bins");
+  MFLOW_REQUIRE((double)d->min_bin_height * d->num_bins <= 1.0, "Minimal bin height too large for the number of bins");
+  a.n = d->n;
+  RqsConsts& c = a.c;
+  const int K = d->num_bins;
+  c.lo = d->left; c.tail = d->right; c.span = (float)((double)d->right - (double)d->left);
+  c.lo_y = d->bottom; c.hi_y = d->top; c.span_y = (float)((double)d->top - (double)d->bottom);
+  c.min_w = d->min_bin_width; c.min_h = d->min_bin_height; c.min_d = d->min_derivative;
+  c.cfac_w = (float)(1.0 - (double)d->min_bin_width * K);
+  c.cfac_h = (float)(1.0 - (double)d->min_bin_height * K);
+  c.edge = 0.f; c.divisor = 1.f; c.rcp_divisor = 1.f; c.use_divisor = 0;
+  return MFLOW_OK;
+}
+
+extern "C" MFLOW_API int mflow_rqs_box_apply(const mflow_rqs_box_desc* d, const float* x, const float* params, float* y, float* lad,
+                                             int32_t* bins, void* stream) {
+  RqsBoxArgs a{};
+  if (int rc = fill_box(d, a)) return rc;
+  if (d->n == 0) return MFLOW_OK;
+  MFLOW_REQUIRE(x && params && y && lad, "null tensor pointer");
+  a.x = x; a.params = params; a.y = y; a.lad = lad; a.bins = bins;
+  const unsigned grid = (unsigned)((d->n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_box_kernel<K, true, false><<<grid, 128, 0, st>>>(a);
+                   else rqs_box_kernel<K, false, false><<<grid, 128, 0, st>>>(a));
+  return check_launch("rqs_box_kernel");
+}
+
+extern "C" MFLOW_API int mflow_rqs_box_backward(const mflow_rqs_box_desc* d, const float* x_in, const float* x_out,
+                                                const float* params, const float* g_out, const float* g_lad, float* g_in,
+                                                float* g_params, void* stream) {
+  RqsBoxArgs a{};
+  if (int rc = fill_box(d, a)) return rc;
+  if (d->n == 0) return MFLOW_OK;
+  MFLOW_REQUIRE(x_in && params && g_in && g_params, "null tensor pointer");
+  MFLOW_REQUIRE(!d->inverse || x_out, "inverse backward needs the output of the apply call");
+  a.x = x_in; a.x_out = x_out; a.params = params; a.y = g_in; a.g_out = g_out; a.g_lad = g_lad; a.g_params = g_params;
+  const unsigned grid = (unsigned)((d->n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_box_kernel<K, true, true><<<grid, 128, 0, st>>>(a);
+                   else rqs_box_kernel<K, false, true><<<grid, 128, 0, st>>>(a));
+  return check_launch("rqs_box_kernel(bwd)");
 }

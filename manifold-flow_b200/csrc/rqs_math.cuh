@@ -34,6 +34,9 @@ struct RqsConsts {
   float divisor;     // widths / heights logits are divided by this (coupling.py:506-511)
   float rcp_divisor; // float(1 / divisor)
   int use_divisor;
+  // box mode only (rational_quadratic_spline on [left, right] x [bottom, top], :67-168): the x axis uses lo / tail /
+  // span above as left / right / right - left, the y axis these
+  float lo_y, hi_y, span_y;
 };
 
 // Correctly rounded x / d for a constant d with pre-rounded reciprocal r (one Newton step on the
@@ -146,9 +149,13 @@ struct RqsBin {
   float sig_w[K], sig_h[K];  // softmax probabilities (backward only)
 };
 
-// p holds the element's 3K-1 raw parameters [widths | heights | derivatives].
-template <int K, bool INV>
-__device__ __forceinline__ void rqs_locate(float v, const float (&p)[3 * K - 1], const RqsConsts& c, RqsBin<K>& b) {
+// p holds the element's raw parameters [widths | heights | derivatives]: NP = 3K-1 for the unconstrained spline
+// with linear tails (K-1 interior derivative logits, the two boundary ones are the constant c.edge, :38-41), or
+// NP = 3K+1 for the spline on a box ("BOX": all K+1 knot derivatives given, separate x and y ranges, :67-168).
+template <int K, bool INV, int NP = 3 * K - 1>
+__device__ __forceinline__ void rqs_locate(float v, const float (&p)[NP], const RqsConsts& c, RqsBin<K>& b) {
+  constexpr bool BOX = NP == 3 * K + 1;
+  static_assert(NP == 3 * K - 1 || NP == 3 * K + 1, "parameter count");
   float uw[K], uh[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -162,7 +169,7 @@ __device__ __forceinline__ void rqs_locate(float v, const float (&p)[3 * K - 1],
   }
   float kw[K + 1], kh[K + 1];
   rqs_axis<K>(uw, c.lo, c.tail, c.span, c.min_w, c.cfac_w, kw, b.sig_w);
-  rqs_axis<K>(uh, c.lo, c.tail, c.span, c.min_h, c.cfac_h, kh, b.sig_h);
+  rqs_axis<K>(uh, BOX ? c.lo_y : c.lo, BOX ? c.hi_y : c.tail, BOX ? c.span_y : c.span, c.min_h, c.cfac_h, kh, b.sig_h);
   float x_lo, x_hi, y_lo, y_hi;
   if (INV) {
     b.k = rqs_search<K>(kh, v, y_lo, y_hi);
@@ -176,12 +183,21 @@ __device__ __forceinline__ void rqs_locate(float v, const float (&p)[3 * K - 1],
   b.yk = y_lo;
   b.hk = __fsub_rn(y_hi, y_lo);
   b.sk = __fdiv_rn(b.hk, b.wk);  // :131
-  b.uk = c.edge;
-  b.uk1 = c.edge;
+  if constexpr (BOX) {
+    b.uk = p[2 * K];
+    b.uk1 = p[2 * K + 1];
 #pragma unroll
-  for (int j = 0; j < K - 1; ++j) {  // padded logits: [edge, D_0 .. D_{K-2}, edge]
-    if (b.k == j + 1) b.uk = p[2 * K + j];
-    if (b.k == j) b.uk1 = p[2 * K + j];
+    for (int j = 1; j < K; ++j) {
+      if (b.k == j) { b.uk = p[2 * K + j]; b.uk1 = p[2 * K + j + 1]; }
+    }
+  } else {
+    b.uk = c.edge;
+    b.uk1 = c.edge;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) {  // padded logits: [edge, D_0 .. D_{K-2}, edge]
+      if (b.k == j + 1) b.uk = p[2 * K + j];
+      if (b.k == j) b.uk1 = p[2 * K + j];
+    }
   }
   b.dk = __fadd_rn(c.min_d, softplus20(b.uk));  // :111
   b.dk1 = __fadd_rn(c.min_d, softplus20(b.uk1));
@@ -197,17 +213,19 @@ __device__ __forceinline__ float rqs_logdet_terms(float sk, float dk, float dk1,
 }
 
 // Evaluate one element.  Outside [-T, T] (closed): identity, logabsdet 0, bin -1 (:31,:43-44).
-template <int K, bool INV>
-__device__ __forceinline__ void rqs_eval(float v, const float (&p)[3 * K - 1], const RqsConsts& c, float& out, float& lad,
+// (BOX: outside the domain of the searched axis; the host wrapper has raised InputOutsideDomain before.)
+template <int K, bool INV, int NP = 3 * K - 1>
+__device__ __forceinline__ void rqs_eval(float v, const float (&p)[NP], const RqsConsts& c, float& out, float& lad,
                                          int& bin) {
-  if (!(v >= c.lo && v <= c.tail)) {
+  constexpr bool BOX = NP == 3 * K + 1;
+  if (!(v >= ((BOX && INV) ? c.lo_y : c.lo) && v <= ((BOX && INV) ? c.hi_y : c.tail))) {
     out = v;
     lad = 0.f;
     bin = -1;
     return;
   }
   RqsBin<K> b;
-  rqs_locate<K, INV>(v, p, c, b);
+  rqs_locate<K, INV, NP>(v, p, c, b);
   bin = b.k;
   const float a_term = __fsub_rn(__fadd_rn(b.dk, b.dk1), __fmul_rn(2.f, b.sk));  // d_k + d_{k+1} - 2 s
   if (INV) {  // :139-156
@@ -238,17 +256,18 @@ __device__ __forceinline__ void rqs_eval(float v, const float (&p)[3 * K - 1], c
 //   v_out : output of the apply call (only used when INV: the x the inverse produced)
 // Inverse direction by implicit differentiation of y = F(x; params), lad_inv = -lad_F(x; params).
 // store(j, value) is called exactly once for every parameter index j in [0, 3K-1).
-template <int K, bool INV, typename Store>
-__device__ __forceinline__ void rqs_grad(float v_in, float v_out, const float (&p)[3 * K - 1], const RqsConsts& c,
+template <int K, bool INV, int NP = 3 * K - 1, typename Store>
+__device__ __forceinline__ void rqs_grad(float v_in, float v_out, const float (&p)[NP], const RqsConsts& c,
                                          float g_out, float g_lad, float& g_in, Store&& store) {
-  if (!(v_in >= c.lo && v_in <= c.tail)) {
+  constexpr bool BOX = NP == 3 * K + 1;
+  if (!(v_in >= ((BOX && INV) ? c.lo_y : c.lo) && v_in <= ((BOX && INV) ? c.hi_y : c.tail))) {
     g_in = g_out;
 #pragma unroll
-    for (int j = 0; j < 3 * K - 1; ++j) store(j, 0.f);
+    for (int j = 0; j < NP; ++j) store(j, 0.f);
     return;
   }
   RqsBin<K> b;
-  rqs_locate<K, INV>(v_in, p, c, b);
+  rqs_locate<K, INV, NP>(v_in, p, c, b);
   const float xdom = INV ? v_out : v_in;
   const float inv_w = 1.f / b.wk;
   const float t = (xdom - b.xk) * inv_w, u = 1.f - t, tt = t * u, umt = u - t;
@@ -305,7 +324,8 @@ __device__ __forceinline__ void rqs_grad(float v_in, float v_out, const float (&
     }
   }
   {  // heights
-    const float lt = c.cfac_h * c.span * g_yk, eq = c.cfac_h * c.span * g_hk;
+    const float span_y = BOX ? c.span_y : c.span;
+    const float lt = c.cfac_h * span_y * g_yk, eq = c.cfac_h * span_y * g_hk;
     float below = 0.f, at = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -320,8 +340,13 @@ __device__ __forceinline__ void rqs_grad(float v_in, float v_out, const float (&
     }
   }
   const float gd0 = g_dk * sigmoid20(b.uk), gd1 = g_dk1 * sigmoid20(b.uk1);
+  if constexpr (BOX) {
 #pragma unroll
-  for (int j = 0; j < K - 1; ++j) store(2 * K + j, (b.k == j + 1) ? gd0 : ((b.k == j) ? gd1 : 0.f));
+    for (int j = 0; j <= K; ++j) store(2 * K + j, (b.k == j) ? gd0 : ((b.k + 1 == j) ? gd1 : 0.f));
+  } else {
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) store(2 * K + j, (b.k == j + 1) ? gd0 : ((b.k == j) ? gd1 : 0.f));
+  }
 }
 
 }  // namespace mflow

@@ -35,6 +35,16 @@ class RqsDesc(ctypes.Structure):
     ]
 
 
+class RqsBoxDesc(ctypes.Structure):
+    """mflow_rqs_box_desc"""
+
+    _fields_ = [
+        ("n", i64), ("num_bins", i32), ("inverse", i32),
+        ("left", f32), ("right", f32), ("bottom", f32), ("top", f32),
+        ("min_bin_width", f32), ("min_bin_height", f32), ("min_derivative", f32),
+    ]
+
+
 class ConvDesc(ctypes.Structure):
     """mflow_conv_desc"""
 
@@ -62,6 +72,8 @@ _SIGNATURES = {
     "mflow_rqs_workspace_bytes": (i64, [ctypes.POINTER(RqsDesc)]),
     "mflow_rqs_apply": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
     "mflow_rqs_backward": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
+    "mflow_rqs_box_apply": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 6),
+    "mflow_rqs_box_backward": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 8),
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
     "mflow_conv2d_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
     "mflow_conv2d_wgrad_workspace_bytes": (i64, [ctypes.POINTER(ConvDesc)]),

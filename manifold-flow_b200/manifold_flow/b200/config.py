@@ -26,4 +26,16 @@ class _Config:
     exact_permutation_jacobian = os.environ.get("MFLOW_EXACT_PERM_JACOBIAN", "0") == "1"
 
 
+    # Bumped by ``invalidate_caches()``: part of the key of every parameter-derived cache (dense L / U, composed channel
+    # mixes, split convolution weights).  Writes through ``.data`` or by collectives do not bump ``Tensor._version``;
+    # whoever writes parameters that way calls ``invalidate_caches()``.
+    cache_epoch = 0
+
+
 config = _Config()
+
+
+def invalidate_caches():
+    """Drop every parameter-derived cache (next use rebuilds).  Called after writes that bypass the version counter:
+    ActNorm's data-dependent initialisation, ``ddp.broadcast_parameters``, and by users who assign ``param.data``."""
+    config.cache_epoch += 1

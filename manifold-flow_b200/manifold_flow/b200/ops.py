@@ -12,7 +12,7 @@ import torch
 
 from . import cabi
 from .config import config
-from .cabi import ConvDesc, MixDesc, RqsDesc, check, lib, ptr, require_cuda, stream
+from .cabi import ConvDesc, MixDesc, RqsBoxDesc, RqsDesc, check, lib, ptr, require_cuda, stream
 
 
 def _c(t):
@@ -183,6 +183,43 @@ def rqs_elementwise(x, params, num_bins, tail_bound, min_w=1e-3, min_h=1e-3, min
                                  bool(return_bins))
 
 
+class _RqsBox(torch.autograd.Function):
+    """Flat [N] inputs with [N, 3K+1] parameter rows on a box [left, right] x [bottom, top]:
+    ``rational_quadratic_spline`` (rational_quadratic.py:67-168)."""
+
+    @staticmethod
+    def forward(ctx, x, params, num_bins, box, mins, inverse, want_bins):
+        require_cuda(x, params)
+        x, params = _c(x), _c(params)
+        d = RqsBoxDesc(n=x.numel(), num_bins=num_bins, inverse=int(bool(inverse)), left=box[0], right=box[1], bottom=box[2], top=box[3],
+                       min_bin_width=mins[0], min_bin_height=mins[1], min_derivative=mins[2])
+        y, lad = torch.empty_like(x), torch.empty_like(x)
+        bins = torch.empty(x.numel(), dtype=torch.int32, device=x.device) if want_bins else None
+        check(lib().mflow_rqs_box_apply(ctypes.byref(d), ptr(x), ptr(params), ptr(y), ptr(lad), ptr(bins), stream()), "mflow_rqs_box_apply")
+        cabi.count_launch()
+        ctx.desc = d
+        ctx.save_for_backward(x, params, y if inverse else None)
+        if want_bins:
+            ctx.mark_non_differentiable(bins)
+            return y, lad, bins
+        return y, lad
+
+    @staticmethod
+    def backward(ctx, g_y, g_lad, *_):
+        x, params, y = ctx.saved_tensors
+        g_x, g_p = torch.empty_like(x), torch.empty_like(params)
+        check(lib().mflow_rqs_box_backward(ctypes.byref(ctx.desc), ptr(x), ptr(y), ptr(params), ptr(None if g_y is None else _c(g_y)),
+                                           ptr(None if g_lad is None else _c(g_lad)), ptr(g_x), ptr(g_p), stream()),
+              "mflow_rqs_box_backward")
+        cabi.count_launch()
+        return (g_x, g_p) + (None,) * 5
+
+
+def rqs_box(x, params, num_bins, left, right, bottom, top, min_w=1e-3, min_h=1e-3, min_d=1e-3, inverse=False, return_bins=False):
+    return _RqsBox.apply(x, params, int(num_bins), (float(left), float(right), float(bottom), float(top)),
+                         (float(min_w), float(min_h), float(min_d)), bool(inverse), bool(return_bins))
+
+
 def rqs_search(knots, values):
     """The kernels' bin search on given knots ([n, K+1], [n]) -> int32 [n] (test entry)."""
     require_cuda(knots, values)
@@ -229,7 +266,7 @@ class _WeightCache:
         bound to the owner, so that a new view object per call does not miss."""
         anchor = weight if owner is None else owner
         key = (id(anchor), transposed)
-        ver = (weight.data_ptr(), anchor._version, tuple(weight.shape))
+        ver = (weight.data_ptr(), anchor._version, tuple(weight.shape), config.cache_epoch)
         ent = self._entries.get(key)
         if ent is None or ent[0]() is not anchor or ent[1] != ver:
             if len(self._entries) > 4096:
@@ -628,6 +665,31 @@ class _GaussLogProb(torch.autograd.Function):
 def gauss_logprob(u, v=None, eps=1.0, clip=None, add0=None, add1=None):
     """logN(u; 0, 1) [+ logN(clamp(v); 0, eps^2)] [+ add0] [+ add1], per row."""
     return _GaussLogProb.apply(u, v, add0, add1, float(eps), float(clip) if clip else 0.0)
+
+
+class _EvalOnly(torch.autograd.Function):
+    """Identity whose backward raises: marks results that carry no derivative in this build (the full-Jacobian
+    likelihood of mode="mf" would need double backward through every kernel - SURVEY.md section 8(f) rank 4)."""
+
+    @staticmethod
+    def forward(ctx, value, anchor, what):
+        ctx.what = what
+        return value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError(
+            f"{ctx.what} is evaluation-only in the B200 build: its gradient needs second-order autograd through the fused "
+            "kernels, which is not implemented.  Train with mode='mf-fixed-manifold' / 'projection' (the --sequential and "
+            "--alternate schedules of experiments/train.py); train_manifold_flow / train_specified_manifold_flow "
+            "(simultaneous M-flow training, train.py:145-156) and the SCANDAL loss are unsupported.")
+
+
+def eval_only(value, anchor, what):
+    """``value`` without a graph when nothing upstream needs one; otherwise a node that fails loudly in backward."""
+    if value is None or not (torch.is_grad_enabled() and anchor is not None and anchor.requires_grad):
+        return value
+    return _EvalOnly.apply(value, anchor, what)
 
 
 def jtj_logdet(jac):

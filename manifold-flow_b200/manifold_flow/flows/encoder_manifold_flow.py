@@ -6,6 +6,7 @@ import torch
 from ..b200 import ops
 from ..transforms import fusion
 from ..transforms.base import _expand_lad
+from .base import host_staged
 from .manifold_flow import ManifoldFlow
 
 
@@ -15,6 +16,7 @@ class EncoderManifoldFlow(ManifoldFlow):
         super().__init__(data_dim, latent_dim, outer_transform, inner_transform, pie_epsilon, apply_context_to_outer, clip_pie)
         self.encoder = encoder
 
+    @host_staged
     def forward(self, x, mode="mf", context=None, return_hidden=False):
         if mode not in ("mf", "projection", "pie", "mf-fixed-manifold"):
             raise ValueError("unsupported mode {!r}".format(mode))
@@ -31,6 +33,7 @@ class EncoderManifoldFlow(ManifoldFlow):
             return x_reco, log_prob, u, h_manifold
         return x_reco, log_prob, u
 
+    @host_staged
     def encode(self, x, context=None):
         fusion.begin_pass(self)
         return self._encode(x, context)[0]

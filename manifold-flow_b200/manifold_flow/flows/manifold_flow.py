@@ -9,7 +9,7 @@ from ..b200 import ops
 from ..transforms import ProjectionSplit, fusion
 from ..transforms.base import _expand_lad
 from ..utils.various import product
-from .base import BaseFlow
+from .base import BaseFlow, host_staged
 
 logger = logging.getLogger(__name__)
 
@@ -39,6 +39,7 @@ class ManifoldFlow(BaseFlow):
         self._report_model_parameters()
 
     # ---- public API ------------------------------------------------------------------------
+    @host_staged
     def forward(self, x, mode="mf", context=None, return_hidden=False):
         """Encode, decode and evaluate the likelihood; returns (x_reco, log_prob, u[, hidden]).
 
@@ -56,16 +57,20 @@ class ManifoldFlow(BaseFlow):
             return x_reco, log_prob, u, torch.cat((h_manifold, h_orthogonal), -1)
         return x_reco, log_prob, u
 
+    @host_staged
     def encode(self, x, context=None):
         fusion.begin_pass(self)
         return self._encode(x, context=context)[0]
 
+    @host_staged
     def decode(self, u, u_orthogonal=None, context=None):
         return self._decode(u, mode="projection", u_orthogonal=u_orthogonal, context=context)[0]
 
+    @host_staged
     def log_prob(self, x, mode="mf", context=None):
         return self.forward(x, mode, context)[1]
 
+    @host_staged
     def sample(self, u=None, n=1, context=None, sample_orthogonal=False):
         if u is None:
             u = self.manifold_latent_distribution.sample(n, context=None)
@@ -93,7 +98,7 @@ class ManifoldFlow(BaseFlow):
         # chain of per-layer Jacobians dx/dh of the outer decoder (base.py:52-69), each layer by one
         # reverse pass per coordinate over the whole batch instead of B*D autograd calls (various.py:22-45)
         x, jac = self.outer_transform._jacobian(h, octx, True)
-        return x, inv_log_det_inner, None, jac, h
+        return ops.eval_only(x, u, 'x_reco of mode="mf"'), inv_log_det_inner, None, jac, h
 
     def _log_prob(self, mode, u, h_orthogonal, log_det_inner, log_det_outer, inv_log_det_inner, inv_log_det_outer, inv_jacobian_outer):
         dist = self.orthogonal_latent_distribution
@@ -105,7 +110,8 @@ class ManifoldFlow(BaseFlow):
         if mode == "mf":  # :140-147
             jac = inv_jacobian_outer[:, :, : self.total_latent_dim]
             half_logdet = 0.5 * ops.jtj_logdet(jac)
-            return ops.gauss_logprob(u.detach(), add0=-half_logdet, add1=-inv_log_det_inner.detach())
+            log_prob = ops.gauss_logprob(u.detach(), add0=-half_logdet, add1=-inv_log_det_inner.detach())
+            return ops.eval_only(log_prob, u, 'log_prob of mode="mf"')
         return None
 
     def _report_model_parameters(self):

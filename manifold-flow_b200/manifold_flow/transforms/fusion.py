@@ -104,7 +104,8 @@ class VersionedCache:
         self._value = None
 
     def get(self, params, build):
-        key = tuple((p.data_ptr(), p._version) for p in params) + (torch.is_grad_enabled() and any(p.requires_grad for p in params),)
+        key = (config.cache_epoch,) + tuple((p.data_ptr(), p._version) for p in params) + (
+            torch.is_grad_enabled() and any(p.requires_grad for p in params),)
         if key[-1]:
             key = key + (current_pass(),)
             if current_pass() == 0:
@@ -133,8 +134,10 @@ class PairGroup:
     def _first_maps(self, inverse, device):
         if self.kind == "actnorm":
             return tuple(t.index_select(0, self._idx[0]) for t in self.pairs[0][0]._an_group.affine_maps(inverse))
-        key = (bool(inverse), str(device))
-        if key not in self._perm_mats:   # constant: the permutation buffers never change
+        # load_state_dict overwrites the permutation buffers in place (version bump): part of the key
+        key = (bool(inverse), str(device), config.cache_epoch) + tuple((p._permutation.data_ptr(), p._permutation._version) for p, _ in self.pairs)
+        if key not in self._perm_mats:
+            self._perm_mats.clear()
             n = self.pairs[0][0]._permutation.numel()
             eye = torch.eye(n, dtype=torch.float32, device=device)
             self._perm_mats[key] = torch.stack([eye[(p._inverse_permutation if inverse else p._permutation).to(device), :]
@@ -160,4 +163,7 @@ class PairGroup:
         params = tuple(p for _, c in self.pairs for p in (c.bias,) + c._lu_params())
         if self.kind == "actnorm":
             params = params + tuple(p for a, _ in self.pairs for p in (a.log_scale, a.shift))
+            params = params + tuple(c.permutation._permutation for _, c in self.pairs)
+        else:
+            params = params + tuple(p._permutation for p, _ in self.pairs)
         return self._composed[bool(inverse)].get(params, build)

@@ -219,9 +219,11 @@ class LUGroup:
         if getattr(first, "permutation", None) is None:
             return None
         device = first.lower_entries.device
-        if self._inv_perm is None or self._inv_perm.device != device:
-            self._inv_perm = torch.stack([layer.permutation._inverse_permutation for layer in self.layers]).to(device)
-        return self._inv_perm
+        key = (str(device),) + tuple((layer.permutation._permutation.data_ptr(), layer.permutation._permutation._version)
+                                     for layer in self.layers)
+        if self._inv_perm is None or self._inv_perm[0] != key:   # load_state_dict rewrites the permutation buffers
+            self._inv_perm = (key, torch.stack([layer.permutation._inverse_permutation for layer in self.layers]).to(device))
+        return self._inv_perm[1]
 
     def affine_maps(self, inverse):
         """Stacked per-pixel affine maps (M [G,n,n], m [G,n], logabsdet [G]) of the members: y = W x[perm] + b forward
@@ -242,7 +244,8 @@ class LUGroup:
                 mat = torch.gather(mat, 1, inv_perm[:, :, None].expand(g, n, n))          # W^-1[inv_perm, :]
             return mat, -torch.bmm(mat, bias[:, :, None]).squeeze(2), -lad
 
-        return self._maps[bool(inverse)].get(self._params() + tuple(layer.bias for layer in self.layers), build)
+        perms = tuple(layer.permutation._permutation for layer in self.layers if getattr(layer, "permutation", None) is not None)
+        return self._maps[bool(inverse)].get(self._params() + tuple(layer.bias for layer in self.layers) + perms, build)
 
 
 def assign_lu_groups(model):

@@ -3,6 +3,7 @@ transform is never constructed by experiments/architectures and is out of scope.
 import torch
 from torch import nn
 
+from ..b200.config import invalidate_caches
 from ..utils import various
 from .base import Transform
 
@@ -63,8 +64,11 @@ class ActNorm(Transform):
             if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
                 torch.distributed.broadcast(log_scale, src=0)
                 torch.distributed.broadcast(shift, src=0)
-            self.log_scale.data.copy_(log_scale)
-            self.shift.data.copy_(shift)
+            # written through the parameters themselves (not .data) so that their version counters move and every
+            # cache keyed on them (composed channel mixes, grouped maps) is rebuilt
+            self.log_scale.copy_(log_scale)
+            self.shift.copy_(shift)
+        invalidate_caches()
         self.initialized = True
 
 

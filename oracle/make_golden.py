@@ -101,6 +101,41 @@ def spline_cases():
     print("spline.npz:", len(case_list), "cases")
 
 
+def spline_box_cases():
+    """``rational_quadratic_spline`` on arbitrary boxes (rational_quadratic.py:67-168): outputs, logabsdet (fp32 / fp64)
+    and the reference's autograd gradients of sum(y) + sum(logabsdet).  Own file and own generator so that the
+    fixtures above stay bit-identical."""
+    out, names = {}, []
+    g = torch.Generator().manual_seed(4242)
+    n = 96
+    for k, (left, right, bottom, top) in ((8, (0.0, 1.0, 0.0, 1.0)), (5, (-2.0, 3.0, -1.0, 0.5)), (11, (-10.0, 10.0, -10.0, 10.0)),
+                                            (3, (1.0, 4.0, -7.0, 9.0)), (16, (-0.5, 0.5, 2.0, 2.5))):
+        name = f"box_K{k}_{left:g}_{right:g}_{bottom:g}_{top:g}"
+        names.append(name)
+        w, h, d = (torch.randn(n, k, generator=g) * 1.5, torch.randn(n, k, generator=g) * 1.5, torch.randn(n, k + 1, generator=g) * 2)
+        x = left + (right - left) * torch.rand(n, generator=g)
+        x[0], x[1] = left, right
+        out[f"{name}/box"] = np.array([left, right, bottom, top], dtype=np.float64)
+        out[f"{name}/x"], out[f"{name}/w"], out[f"{name}/h"], out[f"{name}/d"] = npy(x), npy(w), npy(h), npy(d)
+        for dt, suffix in ((torch.float32, ""), (torch.float64, "64")):
+            xx, ww, hh, dd = (t.to(dt).clone().requires_grad_(True) for t in (x, w, h, d))
+            y, lad = ref_rq.rational_quadratic_spline(xx, ww, hh, dd, inverse=False, left=left, right=right, bottom=bottom, top=top)
+            (y.sum() + lad.sum()).backward()
+            out[f"{name}/fwd_y{suffix}"], out[f"{name}/fwd_lad{suffix}"] = npy(y), npy(lad)
+            out[f"{name}/g_x{suffix}"], out[f"{name}/g_w{suffix}"] = npy(xx.grad), npy(ww.grad)
+            out[f"{name}/g_h{suffix}"], out[f"{name}/g_d{suffix}"] = npy(hh.grad), npy(dd.grad)
+            # inverse on the forward outputs clipped into [max(left, bottom), min(right, top)] when the boxes overlap,
+            # else on fresh points of [bottom, top] (only valid when that lies inside [left, right], :85-86 checks x-range)
+            yy = (bottom + (top - bottom) * torch.rand(n, generator=torch.Generator().manual_seed(k))).to(dt)
+            if bottom >= left and top <= right:
+                xi, ladi = ref_rq.rational_quadratic_spline(yy, ww.detach(), hh.detach(), dd.detach(), inverse=True, left=left, right=right,
+                                                            bottom=bottom, top=top)
+                out[f"{name}/inv_in{suffix}"], out[f"{name}/inv_x{suffix}"], out[f"{name}/inv_lad{suffix}"] = npy(yy), npy(xi), npy(ladi)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "spline_box.npz"), **out)
+    print("spline_box.npz:", len(names), "cases")
+
+
 # ------------------------------------------------------------------ layer-level
 def run_layer(name, layer, x, ctx, out, takes_ctx=True, has_inverse=True):
     layer.eval()
@@ -279,6 +314,7 @@ def model_cases():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     spline_cases()
+    spline_box_cases()
     layer_cases()
     model_cases()
     print("golden fixtures written to", OUT)

@@ -121,6 +121,29 @@ def rqs_from_knots(
     return out, torch.log(dnum) - 2 * torch.log(den), idx
 
 
+def rqs_box(
+    x: Tensor,
+    unnormalized_widths: Tensor,
+    unnormalized_heights: Tensor,
+    unnormalized_derivatives: Tensor,
+    inverse: bool = False,
+    left: float = 0.0,
+    right: float = 1.0,
+    bottom: float = 0.0,
+    top: float = 1.0,
+    min_bin_width: float = MIN_BIN_WIDTH,
+    min_bin_height: float = MIN_BIN_HEIGHT,
+    min_derivative: float = MIN_DERIVATIVE,
+):
+    """``rational_quadratic_spline`` on the box [left, right] x [bottom, top]; rational_quadratic.py:67-168.
+    All K+1 knot derivatives are parameters (:111).  The caller guarantees the domain (:85-86)."""
+    d = min_derivative + F.softplus(unnormalized_derivatives)  # :111
+    cw, w = rqs_knots(unnormalized_widths, left, right, min_bin_width)
+    ch, h = rqs_knots(unnormalized_heights, bottom, top, min_bin_height)
+    y, lad, _ = rqs_from_knots(x, cw, w, ch, h, d, inverse)
+    return y, lad
+
+
 def rqs(
     x: Tensor,
     unnormalized_widths: Tensor,

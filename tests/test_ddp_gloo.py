@@ -75,3 +75,71 @@ def test_shard_batch_covers_everything():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_robust(rank, world, port, out):
+    """(1) zero_grad(set_to_none=True) between steps must not stop the averaging; (2) gradient accumulation
+    with overlap=False; (3) a second backward() with overlap=True fails loudly instead of reducing a half-filled bucket."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "manifold-flow_b200"))
+    from manifold_flow.b200 import ddp
+
+    ddp.init_from_env("gloo")
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(12, 5, generator=g), torch.randn(12, 3, generator=g)
+    lo, hi = ddp.shard_batch(12, rank, world)
+    loss_fn = lambda a, b: ((net(x_all[a:b]) - y_all[a:b]) ** 2).sum() / 12.0
+    res = {}
+    for overlap in (True, False):
+        reducer = ddp.GradientAllReducer(net.parameters(), bucket_mb=0.0002, overlap=overlap)
+        reducer.zero_grad()
+        loss_fn(lo, hi).backward()
+        reducer.finish()
+        net.zero_grad(set_to_none=True)        # what optimizer.zero_grad() does by default: the bucket views are gone
+        loss_fn(lo, hi).backward()             # hooks must re-attach the views and still average
+        reducer.finish()
+        res[f"none_{overlap}"] = [p.grad.clone() * world for p in net.parameters()]   # sum-of-shard-means * 1 = full gradient
+        assert all(reducer._aliases(p) for p in net.parameters())
+        reducer.close()
+    # accumulation over two micro-batches, all-reduce once
+    reducer = ddp.GradientAllReducer(net.parameters(), bucket_mb=0.0002, overlap=False)
+    reducer.zero_grad()
+    mid = (lo + hi) // 2
+    loss_fn(lo, mid).backward()
+    loss_fn(mid, hi).backward()
+    reducer.finish()
+    res["accum"] = [p.grad.clone() * world for p in net.parameters()]
+    reducer.close()
+    # second backward with overlap=True -> loud failure
+    reducer = ddp.GradientAllReducer(net.parameters(), bucket_mb=0.0002, overlap=True)
+    reducer.zero_grad()
+    loss_fn(lo, mid).backward()
+    try:
+        loss_fn(mid, hi).backward()
+        res["raised"] = False
+    except RuntimeError as exc:
+        res["raised"] = "second backward" in str(exc)
+    reducer.finish()
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reducer_survives_set_to_none_and_accumulation(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker_robust, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(12, 5, generator=g), torch.randn(12, 3, generator=g)
+    (((net(x_all) - y_all) ** 2).sum() / 12.0).backward()
+    for key in ("none_True", "none_False", "accum"):
+        for got, p in zip(res[key], net.parameters()):
+            torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-7)
+    assert res["raised"] is True

@@ -274,3 +274,78 @@ def test_large_batch_rows_and_planes(cuda_device):
     x4, ladi4 = ops.rqs_coupling(y4, p4, geom4, k, t, 1e-3, 1e-3, 1e-3, 10.0, True)
     assert float((x4 - xi4).abs().reshape(-1).kthvalue(int(0.9999 * x4.numel()))[0]) < 1e-4
     assert (lad4 + ladi4).abs().max().item() < 5e-2  # 6144 elements per sample
+
+
+# ---- rational_quadratic_spline on an arbitrary box (rational_quadratic.py:67-168) ----
+SB = gu.load_npz("spline_box.npz")
+
+
+@pytest.mark.parametrize("name", [str(c) for c in SB["cases"]])
+def test_box_spline_matches_golden(cuda_device, name):
+    from manifold_flow.transforms.splines import rational_quadratic_spline as spline
+
+    left, right, bottom, top = (float(v) for v in SB[f"{name}/box"])
+    box = dict(left=left, right=right, bottom=bottom, top=top)
+    x, w, h, d = (_t(SB[f"{name}/{k}"], cuda_device).requires_grad_(True) for k in "xwhd")
+    y, lad = spline(x, w, h, d, inverse=False, **box)
+    scale = max(1.0, abs(bottom), abs(top))
+    gu.assert_as_accurate_as_reference(y, _t(SB[f"{name}/fwd_y"]), _t(SB[f"{name}/fwd_y64"]), what="outputs", floor=1e-6 * scale)
+    gu.assert_as_accurate_as_reference(lad, _t(SB[f"{name}/fwd_lad"]), _t(SB[f"{name}/fwd_lad64"]), what="logabsdet", floor=5e-6)
+    torch.testing.assert_close(y.detach().cpu(), _t(SB[f"{name}/fwd_y"]), rtol=RTOL, atol=ATOL * scale)
+    (y.sum() + lad.sum()).backward()
+    for got, key in ((x.grad, "g_x"), (w.grad, "g_w"), (h.grad, "g_h"), (d.grad, "g_d")):
+        gu.assert_grad_as_accurate_as_reference(got, _t(SB[f"{name}/{key}"]), _t(SB[f"{name}/{key}64"]), what=key)
+    # inverse: golden where the reference can run it, and the round trip everywhere
+    if f"{name}/inv_in" in SB:
+        xi, ladi = spline(_t(SB[f"{name}/inv_in"], cuda_device), w.detach(), h.detach(), d.detach(), inverse=True, **box)
+        gu.assert_as_accurate_as_reference(xi, _t(SB[f"{name}/inv_x"]), _t(SB[f"{name}/inv_x64"]), what="inverse outputs",
+                                           floor=1e-6 * max(1.0, abs(left), abs(right)))
+        gu.assert_as_accurate_as_reference(ladi, _t(SB[f"{name}/inv_lad"]), _t(SB[f"{name}/inv_lad64"]), what="inverse logabsdet", floor=2e-5)
+    from manifold_flow.b200 import ops
+
+    params = torch.cat((w, h, d), dim=-1).detach()
+    y2 = y.detach().clamp(bottom, top)
+    xr, ladr = ops.rqs_box(y2, params, w.shape[-1], left, right, bottom, top, inverse=True)
+    torch.testing.assert_close(xr, x.detach(), rtol=1e-4, atol=2e-4 * max(1.0, right - left))
+    torch.testing.assert_close(ladr + lad.detach(), torch.zeros_like(ladr), rtol=0, atol=2e-3)
+
+
+def test_box_spline_domain_and_argument_errors(cuda_device):
+    from manifold_flow.transforms import InputOutsideDomain
+    from manifold_flow.transforms.splines import rational_quadratic_spline as spline
+
+    k = 6
+    w, h, d = torch.zeros(4, k, device=cuda_device), torch.zeros(4, k, device=cuda_device), torch.zeros(4, k + 1, device=cuda_device)
+    x = torch.tensor([0.1, 0.5, 0.9, 1.5], device=cuda_device)
+    with pytest.raises(InputOutsideDomain):   # rational_quadratic.py:85-86
+        spline(x, w, h, d)
+    with pytest.raises(InputOutsideDomain):
+        spline(-x, w, h, d)
+    with pytest.raises(ValueError):           # :90-93
+        spline(x.clamp(0, 1), w, h, d, min_bin_width=0.5)
+    with pytest.raises(ValueError):
+        spline(x.clamp(0, 1), w, h, d[:, :-1])
+    # identity-like default (zero logits): monotone, maps the box ends onto the box ends exactly
+    y, lad = spline(torch.tensor([2.0, 3.0, 5.0], device=cuda_device), w[:3], h[:3], d[:3], left=2.0, right=5.0, bottom=-1.0, top=1.0)
+    assert float(y[0]) == -1.0 and float(y[2]) == 1.0 and float(y[1]) > -1.0
+    e = torch.empty(0, device=cuda_device)
+    y, lad = spline(e, torch.empty(0, k, device=cuda_device), torch.empty(0, k, device=cuda_device), torch.empty(0, k + 1, device=cuda_device))
+    assert y.shape == (0,) and lad.shape == (0,)
+
+
+@pytest.mark.parametrize("k", [2, 3, 7, 9, 13, 15, 20, 24, 32])
+def test_every_bin_count_is_compiled_in(cuda_device, k):
+    """--splinebins is a free integer in the reference (experiments/train.py:60)."""
+    from manifold_flow.b200 import ops
+
+    g = torch.Generator().manual_seed(k)
+    n, t = 3001, 4.0
+    x = torch.randn(n, generator=g) * (t / 2)
+    params = torch.randn(n, 3 * k - 1, generator=g)
+    split = lambda p: (p[:, :k], p[:, k : 2 * k], p[:, 2 * k :])
+    for inverse in (False, True):
+        ref_y, ref_l = oracle.rqs(x.double(), *split(params.double()), inverse, t)
+        r32_y, r32_l = oracle.rqs(x, *split(params), inverse, t)
+        y, lad = ops.rqs_elementwise(x.to(cuda_device), params.to(cuda_device), k, t, inverse=inverse)
+        gu.assert_as_accurate_as_reference(y, r32_y, ref_y, what=f"K={k} outputs")
+        gu.assert_as_accurate_as_reference(lad, r32_l, ref_l, what=f"K={k} logabsdet", floor=5e-6)

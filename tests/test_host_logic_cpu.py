@@ -212,3 +212,110 @@ def test_pair_group_permutation_lu_pairs():
         got_total.backward()
         for (n, pa), (_, pb) in zip(model.named_parameters(), grouped.named_parameters()):
             assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-5), n
+
+
+def _glue_model(kind):
+    from torch import nn
+
+    from manifold_flow import transforms
+
+    if kind == "actnorm":
+        steps = [transforms.CompositeTransform([transforms.ActNorm(12), transforms.OneByOneConvolution(12)]) for _ in range(3)]
+    else:
+        steps = [transforms.CompositeTransform([transforms.RandomPermutation(features=14), transforms.LULinear(14)]) for _ in range(3)]
+    model = nn.ModuleList(steps)
+    for p in model.parameters():
+        p.data.normal_(0.0, 0.3)
+    return model
+
+
+def _composed_maps(model, inverse):
+    from manifold_flow.transforms import fusion
+
+    fusion.begin_pass()
+    out = []
+    for step in model:
+        first = step._transforms[0]
+        out.append(tuple(t[first._pair_index].clone() for t in first._pair_group.composed(inverse)))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["actnorm", "perm"])
+def test_caches_follow_load_state_dict_with_other_permutations(kind):
+    """the permutation buffers are random per construction; after load_state_dict of a checkpoint with other
+    permutations every grouped 1x1 convolution / (permutation, LU) pair must use the NEW permutation."""
+    from manifold_flow import transforms
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(1)
+    a = _glue_model(kind)
+    torch.manual_seed(2)
+    b = _glue_model(kind)           # other weights AND other permutations
+    for m in list(a.modules()) + list(b.modules()):
+        if isinstance(m, transforms.ActNorm):
+            m.initialized = True
+    a.eval(), b.eval()
+    assign_lu_groups(a)
+    assign_lu_groups(b)
+    with torch.no_grad():
+        for inverse in (False, True):
+            _composed_maps(a, inverse)                 # fills every cache of `a` with its own permutations
+        a.load_state_dict(b.state_dict())
+        for inverse in (False, True):
+            for got, want in zip(_composed_maps(a, inverse), _composed_maps(b, inverse)):
+                for g, w in zip(got, want):
+                    assert torch.equal(g, w)
+        if kind == "actnorm":   # the un-paired grouped path (LUGroup.affine_maps) as well
+            conv_a, conv_b = a[0]._transforms[1], b[0]._transforms[1]
+            for inverse in (False, True):
+                for g, w in zip(conv_a._affine_map(inverse), conv_b._affine_map(inverse)):
+                    assert torch.equal(g, w)
+
+
+def test_actnorm_data_init_invalidates_earlier_eval_caches():
+    """eval forward (identity ActNorm maps cached) -> first training forward (data-dependent init writes the
+    parameters) -> eval again WITHOUT an optimizer step must see the initialised statistics."""
+    from manifold_flow import transforms
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(4)
+    model = _glue_model("actnorm")
+    for m in model.modules():
+        if isinstance(m, transforms.ActNorm):
+            m.log_scale.data.zero_(), m.shift.data.zero_()
+    assign_lu_groups(model)
+    model.eval()
+    with torch.no_grad():
+        before = _composed_maps(model, False)
+        x = torch.randn(64, 12, 3, 3) * 3.0 + 1.5
+        for step in model:    # what the first training batch does (normalization.py:134-147)
+            act = step._transforms[0]
+            act.train()
+            act._initialize(x)
+            assert act.initialized and act.log_scale._version > 0
+        model.eval()
+        after = _composed_maps(model, False)
+    for (m0, b0, l0), (m1, b1, l1), step in zip(before, after, model):
+        assert not torch.allclose(m0, m1) and not torch.allclose(l0, l1)
+        act, conv = step._transforms
+        want = conv._affine_map(False)[0] @ torch.diag(torch.exp(act.log_scale))
+        assert torch.allclose(m1, want, atol=1e-5)
+
+
+def test_invalidate_caches_covers_data_writes():
+    """Writes through .data do not bump Tensor._version: ddp.broadcast_parameters (and users) call invalidate_caches()."""
+    from manifold_flow.b200.config import invalidate_caches
+    from manifold_flow.transforms.lu import assign_lu_groups
+
+    torch.manual_seed(6)
+    model = _glue_model("perm")
+    assign_lu_groups(model)
+    with torch.no_grad():
+        before = _composed_maps(model, False)
+        for p in model.parameters():
+            p.data.mul_(0.5)
+        stale = _composed_maps(model, False)
+        assert all(torch.equal(a[0], b[0]) for a, b in zip(before, stale))     # the hazard the epoch exists for
+        invalidate_caches()
+        fresh = _composed_maps(model, False)
+        assert all(not torch.equal(a[0], b[0]) for a, b in zip(before, fresh))
