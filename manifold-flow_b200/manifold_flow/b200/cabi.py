@@ -4,6 +4,7 @@ The library is loaded lazily: building a model (``nn.Module`` construction, ``st
 handling) works on a CPU-only box, but the first kernel call without the library or without a
 CUDA tensor raises - there is no CPU fallback and no eager-PyTorch fallback on this path.
 """
+import contextlib
 import ctypes
 import os
 import threading
@@ -104,23 +105,47 @@ def library_path():
     return _LIB_PATH
 
 
+def _load(path):
+    if not os.path.exists(path):
+        raise MflowError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C manifold-flow_b200/csrc). The B200 path has no CPU or eager fallback."
+        )
+    handle = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype, fn.argtypes = res, args
+    return handle
+
+
 def lib():
     """The loaded library; raises if it was never built (no fallback)."""
     global _lib
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(_LIB_PATH):
-                    raise MflowError(
-                        f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                        "(make -C manifold-flow_b200/csrc). The B200 path has no CPU or eager fallback."
-                    )
-                handle = ctypes.CDLL(_LIB_PATH)
-                for name, (res, args) in _SIGNATURES.items():
-                    fn = getattr(handle, name)
-                    fn.restype, fn.argtypes = res, args
-                _lib = handle
+                _lib = _load(_LIB_PATH)
     return _lib
+
+
+_variants = {}
+
+
+@contextlib.contextmanager
+def library_variant(name):
+    """Run the enclosed calls through ``libmflow_b200_<name>.so`` (same ABI).  ``exact``: the spline kernels compiled with
+    -DMFLOW_RQS_EXACT_ORDER, i.e. every fp32 operation of the reference separately rounded in the reference's order
+    (csrc/rqs_math.cuh) - the parity tests use it to separate algorithmic agreement from the default build's
+    FMA contraction and ex2.approx."""
+    global _lib
+    if name not in _variants:
+        _variants[name] = _load(_LIB_PATH.replace(".so", f"_{name}.so"))
+    prev = lib()
+    _lib = _variants[name]
+    try:
+        yield _lib
+    finally:
+        _lib = prev
 
 
 def check(rc, what=""):

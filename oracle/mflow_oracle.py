@@ -583,8 +583,8 @@ def permutation_jacobian_reference(perm: Tensor, inverse: bool, batch: int, dtyp
     matrix, so parity requires reproducing it [probed: 3-cycle permutation, autograd vs reference]."""
     idx = torch.argsort(perm) if inverse else perm
     n = perm.numel()
-    jac = torch.zeros(n, n, dtype=dtype)
-    jac[idx, torch.arange(n)] = 1.0
+    jac = torch.zeros(n, n, dtype=dtype, device=perm.device)
+    jac[idx, torch.arange(n, device=perm.device)] = 1.0
     return jac.unsqueeze(0).expand(batch, -1, -1)
 
 

