@@ -53,12 +53,10 @@ class Permutation(Transform):
             raise NotImplementedError("full_jacobian is only available for [B, D] inputs")
         idx = self._inverse_permutation if inverse else self._permutation
         n = idx.numel()
+        # ones at [idx[j], j] (the reference's matrix) or at [j, idx[j]] (exact); scatter with a scalar value - an indexed
+        # assignment of 1.0 would stage a CPU scalar tensor, which a CUDA-graph capture of the evaluation rejects
         jac = torch.zeros(n, n, dtype=inputs.dtype, device=inputs.device)
-        cols = torch.arange(n, device=inputs.device)
-        if config.exact_permutation_jacobian:
-            jac[cols, idx] = 1.0
-        else:
-            jac[idx, cols] = 1.0
+        jac.scatter_(1 if config.exact_permutation_jacobian else 0, idx.view(n, 1) if config.exact_permutation_jacobian else idx.view(1, n), 1.0)
         return outputs.detach(), jac.unsqueeze(0).expand(inputs.shape[0], -1, -1)
 
     def _apply_transform(self, inputs, context, inverse):

@@ -206,6 +206,10 @@ def test_conv_at_bench_batch_vs_fp64(cuda_device, case):
 
     ref = run(torch.float64, lambda xx, ww, bb: F.conv2d(F.relu(xx), ww, bb, padding=k // 2))
     got = run(torch.float32, lambda xx, ww, bb: ops.conv_tc(xx, ww, bb, relu_in=True))
+    # y / grad_x reduce over <= 900 terms; grad_w / grad_b over up to 262144 pixels, ~5350 of them per split-K CTA in ONE
+    # fp32 tensor-memory accumulator (the tensor core truncates when it accumulates, so the error grows with the length of
+    # the chain: 3.7e-5 measured for the level-0 3x3 at batch 256; SURVEY appendix C asks 1e-3 for parameter gradients)
     for name, a, r in zip(["y", "grad_x", "grad_w", "grad_b"], got, ref):
-        assert _rel(a, r) <= 2e-5, f"{name}: rel L2 error {_rel(a, r):.2e}"
-        assert float((a.double() - r).abs().max()) <= 2e-4 * float(r.abs().max()), name
+        tol = 1e-4 if name in ("grad_w", "grad_b") else 2e-5
+        assert _rel(a, r) <= tol, f"{name}: rel L2 error {_rel(a, r):.2e}"
+        assert float((a.double() - r).abs().max()) <= 10 * tol * float(r.abs().max()), name
