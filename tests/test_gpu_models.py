@@ -209,10 +209,6 @@ def test_cuda_graph_replay_equals_eager_step(cuda_device, name, batch):
         (-lp.mean()).backward()
         return lp.detach()
 
-    eager = {}
-    for key, (a, c) in (("first", (xd, cd)), ("second", (xd2, cd2))):
-        lp = step(a, c)
-        eager[key] = (lp.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
     sx, sc = xd.clone(), cd.clone()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -225,13 +221,21 @@ def test_cuda_graph_replay_equals_eager_step(cuda_device, name, batch):
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         s_lp = step(sx, sc)
+    replayed = []
     for key, (a, c) in (("first", (xd, cd)), ("second", (xd2, cd2)), ("first", (xd, cd))):
         sx.copy_(a), sc.copy_(c)
         graph.replay()
         torch.cuda.synchronize()
+        replayed.append((key, s_lp.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    # the eager steps come last: backward on the default stream before the capture would tie the parameters' gradient
+    # accumulators to the legacy stream, which a capture on another stream may not wait for
+    eager = {}
+    for key, (a, c) in (("first", (xd, cd)), ("second", (xd2, cd2))):
+        lp = step(a, c)
+        eager[key] = (lp.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    for key, got_lp, got_g in replayed:
         want_lp, want_g = eager[key]
-        assert torch.equal(s_lp, want_lp), f"{key}: replayed log_prob differs from the eager step"
-        got_g = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert torch.equal(got_lp, want_lp), f"{key}: replayed log_prob differs from the eager step"
         assert set(got_g) == set(want_g)
         for k in want_g:
             torch.testing.assert_close(got_g[k], want_g[k], rtol=1e-6, atol=1e-7, msg=lambda m: f"{key} {k}: {m}")
