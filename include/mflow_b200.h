@@ -180,7 +180,7 @@ MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const flo
                            int64_t rows, int64_t n, int32_t inverse, float cut_point, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * (b) Conditioner convolutions on tcgen05 tensor cores (3xTF32: fp32-accurate).
+ * (b) Conditioner convolutions on tcgen05 tensor cores (error-compensated 3-product split: fp32-accurate).
  * Replaces nn.Conv2d 3x3 (pad 1) / 1x1 + bias (+ pre-activation ReLU, + residual, + ReLU) of
  * ConvResidualNet / ConvResidualBlock (manifold_flow/nn/resnet.py:75-142).
  *   x [batch, c_in, height, width] fp32 NCHW contiguous, height == width in {4, 8, 16, 32}
@@ -201,6 +201,23 @@ typedef struct {
 MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
                         const float* bias, const float* residual, const float* gate, float* y, void* stream);
 
+/* The same convolution with fp16 operand halves (tcgen05 kind::f16: the 11 significant bits of TF32 at twice the
+ * tensor-core rate; the default path of the drop-in package).  fp16 has a 5-bit exponent, so both operands carry
+ * power-of-two scales:
+ *   w_hi / w_lo [taps, n_pad, k_pad] fp16: halves of w[tap][co][ci] * 2^s_co with s_co placing the largest magnitude
+ *     of output channel co in [2^13, 2^14); w_unscale [n_pad] fp32 = 2^-s_co (1 for the padding rows)
+ *   in_amax : device scalar max |x| (mflow_absmax, or the out_amax of the launch that produced x); the kernel scales
+ *     x by the power of two that places it in [2^13, 2^14).  NULL = unscaled (|x| must stay within fp16 range)
+ *   out_amax: optional device scalar, ZERO on entry, receives max |y| (bit pattern compared as unsigned)
+ * Everything else as mflow_conv2d_tf32x3; the result agrees with it to the last few ulps of fp32. */
+MFLOW_API int mflow_conv2d_f16x3(const mflow_conv_desc* desc, const float* x, const void* w_hi, const void* w_lo,
+                       const float* w_unscale, const float* in_amax, const float* bias, const float* residual,
+                       const float* gate, float* y, float* out_amax, void* stream);
+
+/* max |x| over n floats (x 16-byte aligned) merged into *out, which the caller zero-initialises: the operand
+ * scale of the fp16-split kernels for tensors whose producer did not publish it. */
+MFLOW_API int mflow_absmax(const float* x, int64_t n, float* out, void* stream);
+
 /* Weight gradient of the same convolutions (autograd of nn.Conv2d in nn/resnet.py:85-142; the reference runs
  * cuDNN / cuBLAS fp32 wgrad kernels):
  *   g_w[co, ci, ky, kx] = sum_{b,h,w} g_y[b, co, h, w] * (relu_in ? relu(x) : x)[b, ci, h + ky - 1, w + kx - 1]
@@ -213,6 +230,10 @@ MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* desc, const float* x, c
 MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv_desc* desc);
 MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* desc, const float* x, const float* g_y, float* g_w,
                               float* g_bias, void* workspace, void* stream);
+/* fp16-operand variant (see mflow_conv2d_f16x3): x_amax / g_amax are device scalars with max |x| / max |g_y|
+ * (NULL = unscaled). */
+MFLOW_API int mflow_conv2d_wgrad_f16x3(const mflow_conv_desc* desc, const float* x, const float* g_y, const float* x_amax,
+                             const float* g_amax, float* g_w, float* g_bias, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Likelihood epilogues.

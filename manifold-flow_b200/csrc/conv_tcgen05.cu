@@ -10,9 +10,18 @@
 //   memory as [channel][pixel + halo]; all nine taps of the stencil are cut out of it.  (The innermost TMA
 //   coordinate must be a multiple of 16 bytes, so the halo box starts 4 pixels to the left.)  The zero
 //   padding of the convolution and of channels 100..127 is TMA's out-of-bounds fill.
-// * fp32 parity on TF32 tensor cores by the 3xTF32 split: a = a_hi + a_lo with a_hi the TF32 truncation;
-//   D += A_hi B_hi + A_lo B_hi + A_hi B_lo.  Weights are split once per optimizer step on the host side of
-//   the ABI.  Activations are handled by the CTA's eight transform warps between TMA arrival and the MMA:
+// * fp32 parity on the tensor cores by an error-compensated operand split, a = a_hi + a_lo, w = w_hi + w_lo,
+//   D += A_hi B_hi + A_lo B_hi + A_hi B_lo (fp32 accumulation in tensor memory), in one of two operand formats
+//   (template parameter F16):
+//     F16 = true  (default path): fp16 halves, kind::f16, K = 16 per instruction - fp16 carries the same 11
+//                 significant bits as TF32 at TWICE the tensor-core rate.  fp16 has a 5-bit exponent, so both operands
+//                 are scaled by powers of two first: the weights per output channel on the host (w_unscale undoes it
+//                 in the epilogue), the activations by a scale derived from their absolute maximum, which the
+//                 producing kernel publishes (out_amax -> the next launch's in_amax) - gradients of 1e-7 and
+//                 activations of 1e4 both land in [2^13, 2^14) at the top and keep 22 significant bits.
+//     F16 = false: TF32 containers (fp32 range, no scaling), kind::tf32, K = 8 per instruction.
+//   Weights are split once per optimizer step on the host side of the ABI.  Activations are handled by the CTA's
+//   eight transform warps between TMA arrival and the MMA:
 //   two threads per pixel (16 channels each) read their channels (conflict-free), apply the
 //   pre-activation ReLU, split, and store A_hi / A_lo straight into TENSOR MEMORY (tcgen05.st, TMEM lane = pixel), from
 //   where the MMA reads its A operand: the NCHW -> [pixel][channel] transposition costs no extra pass
@@ -25,6 +34,7 @@
 //   they split the channels of a step and the column chunks of the epilogue).  Hand-offs through mbarrier rings; tcgen05.commit releases slots.  Two CTAs share an SM so
 //   that one CTA's prologue / epilogue overlaps the other's main loop.
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "mflow_common.cuh"
@@ -38,11 +48,11 @@ using namespace ptx;
 constexpr int kTileM = 128;   // pixels per CTA tile
 constexpr int kTileN = 128;   // accumulator columns (output channels per CTA tile, N extent <= 128)
 constexpr int kBlockK = 32;   // input channels per pipeline step
-constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one weight operand tile (hi or lo)
+constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one 32-channel chunk of the output / aux tile (fp32) in the staging area
 constexpr int kConvThreads = 320;   // 2 control warps + 8 transform / epilogue warps
 constexpr int kXfWarps = 8;
 constexpr int kStagesA = 2;       // activation operand stages in TMEM
-constexpr int kTmemCols = 256;    // 128 accumulator columns + kStagesA x (A_hi 32 + A_lo 32)
+constexpr int kTmemCols = 256;    // 128 accumulator columns + kStagesA x (A_hi + A_lo): 32 + 32 columns (TF32) or 16 + 16 (fp16 pairs)
 constexpr int kMaxStagesB = 4;
 constexpr int kMaxRaw = 2;
 
@@ -68,22 +78,17 @@ struct ConvArgs {
   int ring_bytes;         // weight ring (also the epilogue's staging area): max(n_b x 2 x w_tile_bytes, chunks x 16 KB)
   int aux_mode;           // 0 none, 1 residual add, 2 ReLU mask (gate)
   int aux_chunks;         // 32-channel boxes of the aux tile to fetch (0 when aux_mode == 0)
-  int debug;              // profiling aid (MFLOW_CONV_DEBUG): bit0 skip MMAs, bit1 skip transform math, bit2 skip stores
+  int w_tail_bytes;       // one weight operand tile of the short last channel block (32-byte rows)
+  // fp16 path: operand scaling (see the header comment); all null / unused on the TF32 path
+  const float* in_amax;   // device scalar: absolute maximum of x (null = no scaling: the caller vouches for the range)
+  const float* w_unscale; // [n_pad] 2^-s_n undoing the per-output-channel weight scale
+  float* out_amax;        // device scalar (zero-initialised by the caller) receiving max |y| of this launch, or null
 };
 
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 // round to nearest TF32 (ties away): the tensor core truncates its fp32 inputs, so the low part of the
 // split is pre-rounded to keep the truncation from biasing the sum
 __device__ __forceinline__ float tf32_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
-
-// Debugging aid (MFLOW_CONV_DEBUG bit 3): CTA (0,0) stamps clock64() per pipeline step:
-// [0][s] transform start (stage free), [1][s] transform done, [2][s] MMA issue (operands ready), [3][s] raw box ready (per kb),
-// [4][0] kernel start, [4][1] accumulator complete, [4][2] epilogue done
-__device__ long long g_conv_trace[5][64];
-// ... and every CTA of grid row 0 records {globaltimer at entry, at exit, SM id} (first 4096 CTAs)
-__device__ unsigned long long g_conv_cta[4096][3];
-__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned int sm_id() { unsigned int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 
 // ring cursor without divisions: slot index + phase parity
 struct Ring {
@@ -92,8 +97,9 @@ struct Ring {
   __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kConvThreads, 2)
-conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_whi8,
                    const __grid_constant__ CUtensorMap map_wlo8, const __grid_constant__ CUtensorMap map_aux,
                    const __grid_constant__ CUtensorMap map_y, const ConvArgs a) {
@@ -120,10 +126,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #define s_tmem (*s_tmem_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((a.debug & 8) && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 4096) {
-    g_conv_cta[blockIdx.x][0] = global_ns();
-    g_conv_cta[blockIdx.x][2] = sm_id();
-  }
+  constexpr int kAPart = F16 ? kBlockK / 2 : kBlockK;   // TMEM columns of one part (hi or lo) of an activation stage
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * kTileN;
   const int tiles_per_img = a.imgs_per_tile > 1 ? 1 : a.H / a.rows_per_tile;
@@ -154,7 +157,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const bool t8 = a.tail_k8 && a.k_blocks == 1;
       for (int tap = 0; tap < n_w_pre; ++tap) {
         uint8_t* dst = s_b + tap * 2 * a.w_tile_bytes;
-        mbar_expect_tx(&b_full[tap], t8 ? a.w_tile_bytes / 2 : 2 * a.w_tile_bytes);
+        mbar_expect_tx(&b_full[tap], t8 ? 2 * a.w_tail_bytes : 2 * a.w_tile_bytes);
         tma_load_3d(dst, t8 ? &map_whi8 : &map_whi, &b_full[tap], 0, n0, tap);
         tma_load_3d(dst + a.w_tile_bytes, t8 ? &map_wlo8 : &map_wlo, &b_full[tap], 0, n0, tap);
       }
@@ -165,8 +168,6 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const bool trace = (a.debug & 8) && blockIdx.x == (unsigned)(a.debug >> 8) && blockIdx.y == 0;   // traced CTA: debug >> 8
-  if (trace && threadIdx.x == 0) g_conv_trace[4][0] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -198,9 +199,9 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (kb == 0 && tap < n_w_pre) continue;
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
           if (a.tail_k8 && kb == a.k_blocks - 1) {
-            // last channel block with at most 8 channels: 32-byte rows (32B swizzle) instead of 128-byte ones -
-            // the kernel is bound by the L2 -> shared weight traffic, and this block would be 3/4 zero padding
-            mbar_expect_tx(&b_full[sb.slot], a.w_tile_bytes / 2);
+            // short last channel block (at most 8 TF32 / 16 fp16 channels): 32-byte rows (32B swizzle) instead of full
+            // ones - the kernel is bound by the L2 -> shared weight traffic, and this block would be mostly zero padding
+            mbar_expect_tx(&b_full[sb.slot], 2 * a.w_tail_bytes);
             tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes, &map_whi8, &b_full[sb.slot], kb * kBlockK, n0, tap);
             tma_load_3d(s_b + sb.slot * 2 * a.w_tile_bytes + a.w_tile_bytes, &map_wlo8, &b_full[sb.slot], kb * kBlockK, n0, tap);
           } else {
@@ -225,36 +226,41 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // elect.sync (not lane == 0): the compiler then issues the tcgen05 instructions back to back instead of
     // wrapping each one in a warp-election loop (the MMAs here are only 56 cycles long)
     if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(kTileM, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      const uint32_t idesc = F16 ? idesc_f16(kTileM, a.n_tile, 0, 0) : idesc_tf32(kTileM, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      constexpr int kStepK = F16 ? 16 : 8;   // channels per MMA instruction: 32 bytes of a weight row, 8 TMEM columns of A
       Ring sb(a.n_b), sa(kStagesA);
       for (int kb = 0; kb < a.k_blocks; ++kb) {
         const int valid = min(kBlockK, a.Cin - kb * kBlockK);
-        const int ksteps = (a.debug & 1) ? 0 : (valid + 7) / 8;
+        const int ksteps = (valid + kStepK - 1) / kStepK;
         for (int tap = 0; tap < a.taps; ++tap, sb.next(), sa.next()) {
           const bool first = kb == 0 && tap == 0;
           mbar_wait(&a_full[sa.slot], sa.phase);
           mbar_wait(&b_full[sb.slot], sb.phase);
           tc_fence_after();
-          if (trace && kb * a.taps + tap < 64) g_conv_trace[2][kb * a.taps + tap] = clock64();
-          const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kBlockK, alo = ahi + kBlockK;
+          const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kAPart, alo = ahi + kAPart;
           const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * a.w_tile_bytes);
-          // K-major, 128B-swizzled weight tiles: 8 channels = 32 bytes (2 descriptor units) further along each row
+          // K-major swizzled weight tiles (128-byte rows / 128B swizzle for TF32, 64-byte rows / 64B swizzle for fp16):
+          // one MMA's K extent = 32 bytes (2 descriptor units) further along each row, 8 TMEM columns further in A
           const bool tail8 = a.tail_k8 && kb == a.k_blocks - 1;   // 32-byte rows, 32B swizzle: 8-row groups 256 bytes apart
-          const uint64_t d_bhi = tail8 ? smem_desc(bhi, 16, 256, 6) : smem_desc(bhi, 16, 1024, 2);
-          const uint64_t d_blo = tail8 ? smem_desc(bhi + a.w_tile_bytes, 16, 256, 6) : smem_desc(bhi + a.w_tile_bytes, 16, 1024, 2);
-          if (ksteps == 4) {
+          const uint32_t sbo = F16 ? 512 : 1024, lay = F16 ? 4 : 2;
+          const uint64_t d_bhi = tail8 ? smem_desc(bhi, 16, 256, 6) : smem_desc(bhi, 16, sbo, lay);
+          const uint64_t d_blo = tail8 ? smem_desc(bhi + a.w_tile_bytes, 16, 256, 6) : smem_desc(bhi + a.w_tile_bytes, 16, sbo, lay);
+          auto mma3 = [&](int kk) {
+            if (F16) {
+              umma_f16_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+              umma_f16_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
+              umma_f16_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
+            } else {
+              umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+              umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
+              umma_tf32_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
+            }
+          };
+          if (ksteps == kBlockK / kStepK) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
-              umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
-              umma_tf32_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
-            }
+            for (int kk = 0; kk < kBlockK / kStepK; ++kk) mma3(kk);
           } else {
-            for (int kk = 0; kk < ksteps; ++kk) {
-              umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
-              umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
-              umma_tf32_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
-            }
+            for (int kk = 0; kk < ksteps; ++kk) mma3(kk);
           }
           umma_commit(&a_empty[sa.slot]);  // slots are free again once these MMAs have read them
           umma_commit(&b_empty[sb.slot]);
@@ -273,13 +279,15 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     // The halves alternate pipeline steps (half h owns TMEM stage h): two steps are in flight in different
     // warps, so one warp's gather / split / tcgen05.st latency hides behind the other's.
-    const uint32_t t_a = t_lane + kTileN + half * 2 * kBlockK;
+    const uint32_t t_a = t_lane + kTileN + half * 2 * kAPart;
+    float sa = 1.f, inv_sa = 1.f;   // fp16 path: power-of-two scale of the activation operand and its inverse
+    if (F16) pow2_scale_from_amax(a.in_amax, sa, inv_sa);
     Ring rb(a.n_raw);
     int step = 0, pa = 0;   // step parity; phase of this half's stage
     for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
-      const int nch = (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
+      const int nch = F16 ? (min(kBlockK, a.Cin - kb * kBlockK) + 15) & ~15
+                          : (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
       mbar_wait(&raw_full[rb.slot], rb.phase);
-      if (trace && warp == 2 && lane == 0 && kb < 64) g_conv_trace[3][kb] = clock64();
       const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
         if (step != half) continue;
@@ -287,11 +295,25 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(&a_empty[half], pa ^ 1);
         pa ^= 1;
         tc_fence_after();
-        const int step_id = kb * a.taps + tap;
-        if (trace && (warp == 2 || warp == 6) && lane == 0 && step_id < 64) g_conv_trace[0][step_id] = clock64();
-        // gather the pixel's channels of the tap, optional ReLU, TF32 hi / lo split, and store both parts
-        // into the pixel's TMEM lane (A_hi columns [0,32), A_lo columns [32,64) of the stage)
-        if (!(a.debug & 2)) {
+        // gather the pixel's channels of the tap, optional ReLU, hi / lo split, and store both parts into the
+        // pixel's TMEM lane (A_hi in the first kAPart columns of the stage, A_lo in the next kAPart)
+        if (F16) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {     // 16 channels = 8 columns of packed fp16 pairs per part
+            const int c0 = g * 16;
+            if (c0 < nch) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                float v0 = src[(c0 + 2 * c) * chan_stride], v1 = src[(c0 + 2 * c + 1) * chan_stride];
+                if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                split_f16x2(v0 * sa, v1 * sa, hi[c], lo[c]);
+              }
+              tmem_st_32x8u(t_a + g * 8, hi);
+              tmem_st_32x8u(t_a + kAPart + g * 8, lo);
+            }
+          }
+        } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int c0 = g * 8;
@@ -305,15 +327,14 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 lo[c] = tf32_round(v - hi[c]);
               }
               tmem_st_32x8(t_a + c0, hi);
-              tmem_st_32x8(t_a + kBlockK + c0, lo);
+              tmem_st_32x8(t_a + kAPart + c0, lo);
             }
           }
-          tmem_st_wait();
         }
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[half]);
-        if (trace && (warp == 2 || warp == 6) && lane == 0 && step_id < 64) g_conv_trace[1][step_id] = clock64();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rb.slot]);   // this warp's reads of the box are program-ordered before
@@ -321,12 +342,12 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    if (trace && warp == 2 && lane == 0) g_conv_trace[4][1] = clock64();
     // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
     const int tile_px = a.rows_per_tile * a.W;
     float* stage = reinterpret_cast<float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
     if (a.aux_chunks) mbar_wait(&aux_full, 0);
     const bool issuer = (warp == 2 + 4 * half) && lane == 0;
+    float out_max = 0.f;
 #pragma unroll 1
     for (int c0 = half * 32; c0 < kTileN; c0 += 64) {   // 32-column chunks alternate between the two halves
       if (n0 + c0 >= a.Cout) break;
@@ -338,26 +359,34 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int co = n0 + c0 + j;
-        float r = v[j] + ((a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f);
+        // fp16 path: undo the operand scales (exact powers of two); w_unscale is padded like the weights
+        float r = F16 ? v[j] * (inv_sa * __ldg(a.w_unscale + co)) : v[j];
+        r += (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
         if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
         if (a.relu_out) r = fmaxf(r, 0.f);
         if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
         auxc[j * tile_px] = r;
+        if (co < a.Cout) out_max = fmaxf(out_max, fabsf(r));   // columns >= Cout hold whatever the MMA read past the weight rows
       }
       fence_proxy_async();
       if (half) named_bar_sync<2>(128); else named_bar_sync<1>(128);
-      if (issuer && !(a.debug & 4)) {
+      if (issuer) {
         tma_store_4d(&map_y, reinterpret_cast<const float*>(s_b) + (c0 / 32) * (kStageBytes / 4), 0, h0, n0 + c0, b0);
         tma_store_commit();
       }
+    }
+    if (a.out_amax != nullptr) {
+      // absolute maximum of this launch's output -> the operand scale of the next (fp16-split) consumer.  Pixels beyond
+      // the batch (partial last tile) computed on zero-filled inputs and are clipped by the store: bias-sized at most.
+      const bool in_range = a.imgs_per_tile > 1 ? (b0 + pbl < a.B) : true;
+      const uint32_t m = __reduce_max_sync(0xffffffffu, in_range ? __float_as_uint(out_max) : 0u);
+      if (lane == 0) amax_publish(a.out_amax, __uint_as_float(m));
     }
     if (issuer) tma_store_wait<0>();  // shared memory must stay valid until the stores have read it
   }
   tc_fence_before();
   __syncthreads();
-  if (trace && threadIdx.x == 0) g_conv_trace[4][2] = clock64();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
-  if ((a.debug & 8) && threadIdx.x == 32 && blockIdx.y == 0 && blockIdx.x < 4096) g_conv_cta[blockIdx.x][1] = global_ns();
 }
 #undef acc_full
 #undef aux_full
@@ -369,18 +398,13 @@ constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kStagesA 
 
 using namespace mflow;
 
-// debugging aid, not part of the ABI: copy out the step trace written under MFLOW_CONV_DEBUG=8
-extern "C" MFLOW_API int mflow_debug_conv_ctas(unsigned long long* out12288) {
-  return cudaMemcpyFromSymbol(out12288, g_conv_cta, sizeof(unsigned long long) * 4096 * 3) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
-}
-extern "C" MFLOW_API int mflow_debug_conv_trace(long long* out320) {
-  return cudaMemcpyFromSymbol(out320, g_conv_trace, sizeof(long long) * 5 * 64) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
-}
-
-extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const float* x, const float* w_hi, const float* w_lo,
-                                             const float* bias, const float* residual, const float* gate, float* y,
-                                             void* stream) {
+// shared host side of both operand formats
+template <bool F16>
+static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_hi, const void* w_lo, const float* w_unscale,
+                       const float* in_amax, const float* bias, const float* residual, const float* gate, float* y, float* out_amax,
+                       void* stream) {
   MFLOW_REQUIRE(d && x && w_hi && w_lo && y, "null pointer");
+  MFLOW_REQUIRE(!F16 || w_unscale, "the fp16 path needs the per-channel weight unscale vector");
   MFLOW_REQUIRE(!(residual && gate), "residual and gate cannot be combined in one call");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
   MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
@@ -389,9 +413,12 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   MFLOW_REQUIRE(d->k_pad % kBlockK == 0 && d->k_pad >= d->c_in && d->n_pad % kTileN == 0 && d->n_pad >= d->c_out,
                 "weights must be padded to [taps][n_pad %% 128 == 0][k_pad %% 32 == 0]");
   if (d->batch == 0) return MFLOW_OK;
+  constexpr int wsz = F16 ? 2 : 4;           // bytes per weight element
+  constexpr int kTailK = F16 ? 16 : 8;       // channels in a 32-byte weight row
   const int W = (int)d->width, H = (int)d->height, B = (int)d->batch;
   ConvArgs a{};
   a.y = y; a.bias = bias; a.residual = residual; a.gate = gate;
+  a.in_amax = in_amax; a.w_unscale = w_unscale; a.out_amax = out_amax;
   a.B = B; a.Cin = (int)d->c_in; a.Cout = (int)d->c_out; a.H = H; a.W = W;
   a.taps = d->kernel == 3 ? 9 : 1;
   a.relu_in = d->relu_in; a.relu_out = d->relu_out;
@@ -404,13 +431,13 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   a.raw_tx = a.box_w * a.box_h * kBlockK * a.imgs_per_tile * 4;
   a.raw_bytes = (a.raw_tx + 1023) / 1024 * 1024;
   a.n_tile = a.Cout <= 112 ? 112 : 128;
-  { const char* dbg = getenv("MFLOW_CONV_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
   // Weight tiles: only the rows that hold output channels travel (rounded up to the 8-row swizzle atom); the
   // MMA's N extent may reach past them into whatever follows in shared memory - those accumulator columns
   // belong to channels >= C_out and are never stored.
   const int n_here_max = a.Cout < kTileN ? a.Cout : kTileN;
   const int w_rows = (n_here_max + 7) / 8 * 8;
-  a.w_tile_bytes = w_rows * kBlockK * 4;
+  a.w_tile_bytes = w_rows * kBlockK * wsz;
+  a.w_tail_bytes = w_rows * 32;
   a.aux_mode = residual ? 1 : (gate ? 2 : 0);
   const int out_chunks = (n_here_max + 31) / 32;   // the output (and aux) tile is staged in the weight ring, 16 KB per 32 channels
   a.aux_chunks = a.aux_mode ? out_chunks : 0;
@@ -427,10 +454,10 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     return r > o ? r : o;
   };
   auto total = [&](int n_raw, int n_b) { return rings(n_raw, n_b) + kConvBarrierBytes; };
-  const int prefs[][2] = {{2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
+  const int prefs[][2] = {{2, 4}, {2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
   a.n_b = 0;
   for (auto& pr : prefs)
-    if (total(pr[0], pr[1]) <= two_cta_budget) { a.n_raw = pr[0]; a.n_b = pr[1]; break; }
+    if ((F16 || pr[1] < 4 || pr[0] == 1) && total(pr[0], pr[1]) <= two_cta_budget) { a.n_raw = pr[0]; a.n_b = pr[1]; break; }
   if (a.n_b == 0) {
     a.n_raw = 2; a.n_b = kMaxStagesB;
     while (a.n_b > 2 && total(a.n_raw, a.n_b) > one_cta_budget) --a.n_b;
@@ -438,13 +465,11 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
   }
   if (a.n_b > steps) a.n_b = steps;
   if (a.n_raw > a.k_blocks) a.n_raw = a.k_blocks;
-  { const char* e = getenv("MFLOW_CONV_NB"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxStagesB) a.n_b = atoi(e); }
-  { const char* e = getenv("MFLOW_CONV_NRAW"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxRaw) a.n_raw = atoi(e); }
   a.ring_bytes = rings(a.n_raw, a.n_b) - a.n_raw * a.raw_bytes;   // weight ring, padded when the staging tile needs more
   MFLOW_REQUIRE(total(a.n_raw, a.n_b) <= one_cta_budget, "tile does not fit in shared memory");
 
   CUtensorMap mx, mhi, mlo, mhi8, mlo8, maux, my;
-  { const int tail = a.Cin % kBlockK; a.tail_k8 = (tail > 0 && tail <= 8 && !getenv("MFLOW_CONV_NO_TAIL8")) ? 1 : 0; }
+  { const int tail = a.Cin % kBlockK; a.tail_k8 = (tail > 0 && tail <= kTailK) ? 1 : 0; }
   {  // output, NCHW: box {W, rows, 32 channels, images}
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
@@ -464,24 +489,69 @@ extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const flo
     cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.box_h, (cuuint32_t)kBlockK, (cuuint32_t)a.imgs_per_tile};
     if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
-  {  // weights: [taps][n_pad][k_pad], K-major 128B-swizzled tiles of n_tile x 32
+  {  // weights: [taps][n_pad][k_pad], K-major swizzled tiles of w_rows x 32 channels (TF32: 128-byte rows, fp16: 64-byte rows)
+    const CUtensorMapDataType dt = F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     cuuint64_t dims[3] = {(cuuint64_t)d->k_pad, (cuuint64_t)d->n_pad, (cuuint64_t)a.taps};
-    cuuint64_t str[2] = {(cuuint64_t)d->k_pad * 4, (cuuint64_t)d->k_pad * d->n_pad * 4};
+    cuuint64_t str[2] = {(cuuint64_t)d->k_pad * wsz, (cuuint64_t)d->k_pad * d->n_pad * wsz};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)w_rows, 1};
-    if (!encode(&mhi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
-    if (!encode(&mlo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
-    cuuint32_t box8[3] = {8u, (cuuint32_t)w_rows, 1};
-    if (!encode(&mhi8, w_hi, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B)) return MFLOW_E_BADARG;
-    if (!encode(&mlo8, w_lo, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B)) return MFLOW_E_BADARG;
+    const CUtensorMapSwizzle sw = F16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (!encode(&mhi, w_hi, 3, dims, str, box, sw, dt)) return MFLOW_E_BADARG;
+    if (!encode(&mlo, w_lo, 3, dims, str, box, sw, dt)) return MFLOW_E_BADARG;
+    cuuint32_t box8[3] = {(cuuint32_t)kTailK, (cuuint32_t)w_rows, 1};
+    if (!encode(&mhi8, w_hi, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B, dt)) return MFLOW_E_BADARG;
+    if (!encode(&mlo8, w_lo, 3, dims, str, box8, CU_TENSOR_MAP_SWIZZLE_32B, dt)) return MFLOW_E_BADARG;
   }
   const int n_tiles = a.imgs_per_tile > 1 ? (B + a.imgs_per_tile - 1) / a.imgs_per_tile : B * (H / a.rows_per_tile);
   dim3 grid(n_tiles, (a.Cout + kTileN - 1) / kTileN);
   const size_t smem = (size_t)total(a.n_raw, a.n_b);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
+  // the opt-in shared-memory limit is a per-device function attribute
+  static size_t attr_smem[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem > attr_smem[dev]) {
+    cudaFuncSetAttribute(conv_split3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_cta_budget);
+    attr_smem[dev] = one_cta_budget;
   }
-  conv_tf32x3_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a);
-  return check_launch("conv_tf32x3_kernel");
+  conv_split3_kernel<F16><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a);
+  return check_launch(F16 ? "conv_split3_kernel<fp16>" : "conv_split3_kernel<tf32>");
+}
+
+extern "C" MFLOW_API int mflow_conv2d_tf32x3(const mflow_conv_desc* d, const float* x, const float* w_hi, const float* w_lo,
+                                             const float* bias, const float* residual, const float* gate, float* y,
+                                             void* stream) {
+  return launch_conv<false>(d, x, w_hi, w_lo, nullptr, nullptr, bias, residual, gate, y, nullptr, stream);
+}
+
+extern "C" MFLOW_API int mflow_conv2d_f16x3(const mflow_conv_desc* d, const float* x, const void* w_hi, const void* w_lo,
+                                            const float* w_unscale, const float* in_amax, const float* bias, const float* residual,
+                                            const float* gate, float* y, float* out_amax, void* stream) {
+  return launch_conv<true>(d, x, w_hi, w_lo, w_unscale, in_amax, bias, residual, gate, y, out_amax, stream);
+}
+
+// max |x| over n floats -> *out (zero-initialised by the caller; bits compared as unsigned): the operand scale of the
+// fp16-split kernels for tensors whose producer did not publish it
+namespace mflow {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t n, float* out) {
+  float m = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream4(x4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[n4 * 4 + threadIdx.x]));
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) ptx::amax_publish(out, __uint_as_float(w));
+}
+}  // namespace mflow
+
+extern "C" MFLOW_API int mflow_absmax(const float* x, int64_t n, float* out, void* stream) {
+  MFLOW_REQUIRE(x && out && n >= 0, "null pointer");
+  MFLOW_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  if (n == 0) return MFLOW_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  return check_launch("absmax_kernel");
 }

@@ -2,6 +2,7 @@
 // kernels: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (TMEM alloc, UMMA, commit, ld).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -147,6 +148,18 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 inputs, fp32 accumulate), A from tensor memory: 128 lanes x K/2 32-bit columns, two fp16 values per
+// column (element 2c in the low half of column c), B from a shared-memory descriptor; K = 16 per instruction
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued UMMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -203,6 +216,12 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const float (&v)[8]
                "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+// raw 32-bit registers (packed fp16 pairs) -> 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_st_32x8u(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------
@@ -224,6 +243,46 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 with fp16 A and B (a_format = b_format = 0), fp32 accumulate; N % 16 == 0 for M = 128
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- fp16 split of a scaled fp32 value pair (error-compensated products on the fp16 tensor-core path) -------------
+// v = hi + lo with hi = fp16(v) and lo = fp16(v - hi): 22 significant bits as long as v's magnitude keeps lo normal,
+// which the callers arrange by scaling their operand with a power of two derived from its absolute maximum.
+// Returns the packed pairs {a in the low half, b in the high half}.
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Power-of-two operand scale from the operand's absolute maximum (a device scalar written by the producer kernel or
+// by absmax_kernel): the maximum lands in [2^13, 2^14), so hi never overflows fp16 (65504) and lo = O(2^-11 hi) stays a
+// normal fp16 number for every element within 2^-17 of the maximum.  scale / inv are exact powers of two.
+__device__ __forceinline__ void pow2_scale_from_amax(const float* amax_ptr, float& scale, float& inv) {
+  scale = 1.f;
+  inv = 1.f;
+  if (amax_ptr == nullptr) return;
+  const float amax = *amax_ptr;
+  if (!(amax > 0.f)) return;   // all-zero operand (or NaN): nothing to scale
+  int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  scale = __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+  inv = __uint_as_float((uint32_t)(127 - 13 + e) << 23);
+}
+
+// running absolute maximum of a kernel's outputs -> device scalar (zero-initialised by the host), as raw bits:
+// non-negative floats order like unsigned integers
+__device__ __forceinline__ void amax_publish(float* slot, float block_max) {
+  const uint32_t bits = __float_as_uint(block_max);
+  if (bits > *reinterpret_cast<volatile uint32_t*>(slot)) atomicMax(reinterpret_cast<unsigned int*>(slot), bits);
 }
 
 }  // namespace ptx

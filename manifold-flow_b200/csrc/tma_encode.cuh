@@ -1,4 +1,4 @@
-// Host-side helper: build a CUtensorMap (fp32, tiled mode) through the driver entry point, without linking libcuda.
+// Host-side helper: build a CUtensorMap (fp32 by default, tiled mode) through the driver entry point, without linking libcuda.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,11 +24,11 @@ inline EncodeTiledFn get_encode() {
 }
 
 inline bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box, CUtensorMapSwizzle sw) {
+                   const cuuint32_t* box, CUtensorMapSwizzle sw, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return false; }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return false; }
   return true;

@@ -17,7 +17,11 @@
 //   column offset of the MMA - measured: "misaligned address").  The vertical tap is the row the TMA box is
 //   taken from; out-of-bounds rows and columns are TMA zero fill = the convolution's padding.  ReLU and the
 //   hi / lo split happen on the way.
-// * 3xTF32: D += P_hi Q_hi + P_lo Q_hi + P_hi Q_lo with fp32 accumulation in TMEM (fp32-level accuracy).
+// * Error-compensated split, D += P_hi Q_hi + P_lo Q_hi + P_hi Q_lo with fp32 accumulation in TMEM (fp32-level
+//   accuracy), in TF32 containers (kind::tf32, K = 8) or - template parameter F16, the default path - in fp16 halves
+//   (kind::f16, K = 16: the same 11 significant bits at twice the tensor-core rate).  fp16's 5-bit exponent is dealt with
+//   by scaling each operand with a power of two derived from its absolute maximum (x_amax / g_amax, published by the
+//   kernels that produced the tensors); the scales are undone when the partials are written.
 // * Split-K: CTA (ks, dy) reduces its share of the pixel blocks for the three taps of kernel row dy into
 //   three TMEM accumulators and writes a partial [tap][ci][co]; a second kernel adds the partials in index
 //   order (deterministic) and writes g_w in the reference's [co][ci][ky][kx] layout.
@@ -54,6 +58,8 @@ struct WgradArgs {
   int n_blocks;     // B * blocks_per_img
   int n_dy;         // 3 (3x3) or 1
   int tmem_cols;
+  const float* x_amax;   // fp16 path: device scalars with max |x| / max |g_y| (null = no scaling)
+  const float* g_amax;
 };
 
 __device__ __forceinline__ float wg_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -65,9 +71,12 @@ struct WgRing {
   __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 
-template <int kW, int kTaps>
+// fp16 path: where the split Q tiles live inside a Q slot (the TMA-loaded fp32 tile occupies the first 16 KB)
+constexpr int kWgQHiOff = kWgQBytes, kWgQLoOff = kWgQBytes + kWgQBytes / 2;
+
+template <int kW, int kTaps, bool F16>
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgradArgs a) {
+wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;                                   // kWgQSlots x {Q_hi 16 KB, Q_lo 16 KB}
@@ -86,6 +95,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int blk0 = ks * per + min(ks, extra), n_my = per + (ks < extra ? 1 : 0);
   constexpr int taps_here = kTaps == 9 ? 3 : 1;
   constexpr int pad = kTaps == 9 ? 1 : 0;
+  constexpr int kPPart = F16 ? kWgPCols / 2 : kWgPCols;   // TMEM columns of one part (hi or lo) of a P stage
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
@@ -123,7 +133,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(128, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      const uint32_t idesc = F16 ? idesc_f16(128, a.n_tile, 0, 0) : idesc_tf32(128, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
       WgRing rq(kWgQSlots);
       int sp = 0, pp = 0;   // P stage and its phase; one stage per (block, tap) work item
       for (int i = 0; i < n_my; ++i, rq.next()) {
@@ -131,22 +141,31 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t qhi = smem_u32(s_q + rq.slot * 2 * kWgQBytes);
         // 8..32-wide maps: one K-major tile [n_tile][128 B], 128B swizzle.  4x4 maps: the TMA box {16 px, n_tile, 2 images}
         // lands as two tiles [n_tile][64 B] (64B swizzle), k-steps 0,1 in the first image's tile and 2,3 in the second's.
+        // fp16: the Q-split warps wrote ONE K-major tile [n_tile][32 px x 2 B = 64 B] (64B swizzle) per part, whatever kW
         auto q_desc = [&](uint32_t base, int kk) -> uint64_t {
+          if (F16) return smem_desc(base + kk * 32, 16, 512, 4);
           if (kW == 4) return smem_desc(base + (kk >> 1) * (a.n_tile * 64) + (kk & 1) * 32, 16, 512, 4);
           return smem_desc(base + kk * 32, 16, 1024, 2);
         };
+        const uint32_t q_hi_base = F16 ? qhi + kWgQHiOff : qhi, q_lo_base = F16 ? qhi + kWgQLoOff : qhi + kWgQBytes;
 #pragma unroll
         for (int t = 0; t < taps_here; ++t) {
           mbar_wait(&p_full[sp], pp);
           tc_fence_after();
           const uint32_t acc = tmem + t * a.n_tile;
-          const uint32_t phi = tmem_p + sp * 2 * kWgPCols, plo = phi + kWgPCols;
+          const uint32_t phi = tmem_p + sp * 2 * kPPart, plo = phi + kPPart;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t d_qhi = q_desc(qhi, kk), d_qlo = q_desc(qhi + kWgQBytes, kk);
-            umma_tf32_ts(acc, phi + kk * 8, d_qhi, idesc, (i == 0 && kk == 0) ? 0u : 1u);
-            umma_tf32_ts(acc, plo + kk * 8, d_qhi, idesc, 1);
-            umma_tf32_ts(acc, phi + kk * 8, d_qlo, idesc, 1);
+          for (int kk = 0; kk < (F16 ? 2 : 4); ++kk) {   // 32 pixels = 2 x K16 (fp16) or 4 x K8 (TF32)
+            const uint64_t d_qhi = q_desc(q_hi_base, kk), d_qlo = q_desc(q_lo_base, kk);
+            if (F16) {
+              umma_f16_ts(acc, phi + kk * 8, d_qhi, idesc, (i == 0 && kk == 0) ? 0u : 1u);
+              umma_f16_ts(acc, plo + kk * 8, d_qhi, idesc, 1);
+              umma_f16_ts(acc, phi + kk * 8, d_qlo, idesc, 1);
+            } else {
+              umma_tf32_ts(acc, phi + kk * 8, d_qhi, idesc, (i == 0 && kk == 0) ? 0u : 1u);
+              umma_tf32_ts(acc, plo + kk * 8, d_qhi, idesc, 1);
+              umma_tf32_ts(acc, phi + kk * 8, d_qlo, idesc, 1);
+            }
           }
           umma_commit(&p_empty[sp]);
           sp ^= 1;
@@ -161,7 +180,9 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int quad = warp & 3, set = (warp - 2) >> 2;
     const int ch = quad * 32 + lane;                          // channel within the p tile = TMEM lane
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-    const uint32_t t_p = tmem_p + t_lane + set * 2 * kWgPCols;
+    const uint32_t t_p = tmem_p + t_lane + set * 2 * kPPart;
+    float sx = 1.f, inv_sx = 1.f, sg = 1.f, inv_sg = 1.f;   // fp16 path: power-of-two operand scales
+    if (F16) { pow2_scale_from_amax(a.x_amax, sx, inv_sx); pow2_scale_from_amax(a.g_amax, sg, inv_sg); }
 
     WgRing rp(a.n_raw);
     int pp = 0, item = 0;   // phase of this set's stage; running (block, tap) work item: set s takes the items of parity s
@@ -191,19 +212,32 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         pp ^= 1;
         tc_fence_after();
         // the 32 pixels shifted by this tap (x offset t - 1; box column = w + 4), ReLU, hi / lo split -> TMEM
+        auto pixel = [&](int px) -> float {
+          float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];   // rows of both images are consecutive in raw[]
+          return a.relu_in ? fmaxf(v, 0.f) : v;
+        };
+        if (F16) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float h8[8], l8[8];
+          for (int j = 0; j < 2; ++j) {   // 16 pixels = 8 columns of packed fp16 pairs per part
+            uint32_t h8[8], l8[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int px = 8 * j + c;
-            float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];   // rows of both images are consecutive in raw[]
-            if (a.relu_in) v = fmaxf(v, 0.f);
-            h8[c] = wg_trunc(v);
-            l8[c] = wg_round(v - h8[c]);
+            for (int c = 0; c < 8; ++c) split_f16x2(pixel(16 * j + 2 * c) * sx, pixel(16 * j + 2 * c + 1) * sx, h8[c], l8[c]);
+            tmem_st_32x8u(t_p + 8 * j, h8);
+            tmem_st_32x8u(t_p + kPPart + 8 * j, l8);
           }
-          tmem_st_32x8(t_p + 8 * j, h8);
-          tmem_st_32x8(t_p + kWgPCols + 8 * j, l8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float h8[8], l8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float v = pixel(8 * j + c);
+              h8[c] = wg_trunc(v);
+              l8[c] = wg_round(v - h8[c]);
+            }
+            tmem_st_32x8(t_p + 8 * j, h8);
+            tmem_st_32x8(t_p + kPPart + 8 * j, l8);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -219,6 +253,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int ci = p0 + ch;
     const int n_here = min(128, a.Cout - q0);
     const int n_chunks = (n_here + 31) / 32;
+    const float unscale = inv_sx * inv_sg;   // exact: both are powers of two (1 on the TF32 path)
     for (int t = 0; t < taps_here; ++t) {
       const int tap = kTaps == 9 ? dy * 3 + t : 0;
       float* dst = a.partial + (((int64_t)ks * a.taps + tap) * a.Cin + ci) * a.Cout + q0;
@@ -228,7 +263,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (ci < a.Cin) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < n_here) dst[c * 32 + j] = v[j];
+            if (c * 32 + j < n_here) dst[c * 32 + j] = F16 ? v[j] * unscale : v[j];
         }
       }
     }
@@ -242,21 +277,45 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const bool do_bias = a.bias_partial != nullptr && dy == (kTaps == 9 ? 1 : 0) && p0 == 0;
     float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // n_vec <= 1024 = 8 x 128
     int last_slot = 0;
+    float sg = 1.f, inv_sg = 1.f;
+    if (F16) pow2_scale_from_amax(a.g_amax, sg, inv_sg);
     for (int i = 0; i < n_my; ++i, rq.next()) {
       mbar_wait(&qraw_full[rq.slot], rq.phase);
       float4* hi = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes);
       float4* lo = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes + kWgQBytes);
+      uint8_t* f16_hi = s_q + rq.slot * 2 * kWgQBytes + kWgQHiOff;
+      uint8_t* f16_lo = s_q + rq.slot * 2 * kWgQBytes + kWgQLoOff;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int j = tid + 128 * k;
         if (j < n_vec) {
           const float4 v = hi[j];
           bsum[k] += (v.x + v.y) + (v.z + v.w);
-          float4 h, l;
-          h.x = wg_trunc(v.x); h.y = wg_trunc(v.y); h.z = wg_trunc(v.z); h.w = wg_trunc(v.w);
-          l.x = wg_round(v.x - h.x); l.y = wg_round(v.y - h.y); l.z = wg_round(v.z - h.z); l.w = wg_round(v.w - h.w);
-          hi[j] = h;
-          lo[j] = l;
+          if (F16) {
+            // float4 j of the TMA-swizzled fp32 tile -> (row r, 4-pixel group c8 of the 32-pixel block) -> 8 bytes of the
+            // fp16 K-major tile [n_tile][64 B] with the 64B swizzle (16-byte chunk index ^= (row >> 1) & 3)
+            int r, c8;
+            if (kW == 4) {   // two fp32 tiles [n_tile][16 px] (64B swizzle), one per image: block pixel = 16 * image + px
+              const int img = j / (a.n_tile * 4), jj = j - img * (a.n_tile * 4);
+              r = jj >> 2;
+              c8 = 4 * img + ((jj & 3) ^ ((r >> 1) & 3));
+            } else {         // one fp32 tile [n_tile][32 px] (128B swizzle)
+              r = j >> 3;
+              c8 = (j & 7) ^ (r & 7);
+            }
+            uint2 h, l;
+            split_f16x2(v.x * sg, v.y * sg, h.x, l.x);
+            split_f16x2(v.z * sg, v.w * sg, h.y, l.y);
+            const int off = r * 64 + (((c8 >> 1) ^ ((r >> 1) & 3)) << 4) + ((c8 & 1) << 3);
+            *reinterpret_cast<uint2*>(f16_hi + off) = h;
+            *reinterpret_cast<uint2*>(f16_lo + off) = l;
+          } else {
+            float4 h, l;
+            h.x = wg_trunc(v.x); h.y = wg_trunc(v.y); h.z = wg_trunc(v.z); h.w = wg_trunc(v.w);
+            l.x = wg_round(v.x - h.x); l.y = wg_round(v.y - h.y); l.z = wg_round(v.z - h.z); l.w = wg_round(v.w - h.w);
+            hi[j] = h;
+            lo[j] = l;
+          }
         }
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
@@ -351,8 +410,9 @@ extern "C" MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv
   return (int64_t)wgrad_splits(d) * (taps * d->c_in * d->c_out + d->c_out) * (int64_t)sizeof(float);
 }
 
-extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, const float* x, const float* g_y, float* g_w,
-                                                   float* g_bias, void* workspace, void* stream) {
+template <bool F16>
+static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g_y, const float* x_amax, const float* g_amax,
+                        float* g_w, float* g_bias, void* workspace, void* stream) {
   MFLOW_REQUIRE(d && x && g_y && g_w && workspace, "null pointer");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
   MFLOW_REQUIRE(d->width == 32 || d->width == 16 || d->width == 8 || d->width == 4, "width must be 4, 8, 16 or 32");
@@ -377,6 +437,7 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   // one n_tile for the whole launch: a multiple of 16 covering the widest q tile
   { const int widest = a.Cout < 128 ? a.Cout : 128; a.n_tile = (widest + 15) / 16 * 16; }
   a.tmem_cols = 512;
+  a.x_amax = x_amax; a.g_amax = g_amax;
   MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + 4 * kWgPCols <= 512, "accumulators do not fit in tensor memory");
   const int n_ks = wgrad_splits(d);
   a.bias_partial = g_bias ? a.partial + (int64_t)n_ks * a.taps * a.Cin * a.Cout : nullptr;
@@ -397,14 +458,16 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   dim3 grid(n_ks, a.n_dy, q_tiles * p_tiles);
   const size_t smem = (size_t)kWgQSlots * 2 * kWgQBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
   const cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
 #define MFLOW_WGRAD_LAUNCH(WW, TT)                                                                                   \
   do {                                                                                                               \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      cudaFuncSetAttribute(wgrad_tf32x3_kernel<WW, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);    \
-      attr_set = true;                                                                                               \
+    static bool attr_set[64] = {};   /* the opt-in shared-memory limit is a per-device function attribute */         \
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {                                                                    \
+      cudaFuncSetAttribute(wgrad_split3_kernel<WW, TT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+      attr_set[dev] = true;                                                                                          \
     }                                                                                                                \
-    wgrad_tf32x3_kernel<WW, TT><<<grid, kWgThreads, smem, st>>>(mx, mg, a);                                          \
+    wgrad_split3_kernel<WW, TT, F16><<<grid, kWgThreads, smem, st>>>(mx, mg, a);                                     \
   } while (0)
   if (a.taps == 9) {
     if (W == 32) MFLOW_WGRAD_LAUNCH(32, 9); else if (W == 16) MFLOW_WGRAD_LAUNCH(16, 9); else if (W == 8) MFLOW_WGRAD_LAUNCH(8, 9);
@@ -418,5 +481,15 @@ extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, con
   int64_t rblocks = (n_out + a.Cout + 31) / 32;
   const int rgrid = (int)(rblocks > 16 * kNumSMs ? 16 * kNumSMs : rblocks);
   wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(a.partial, g_w, n_ks, a.taps, a.Cin, a.Cout, a.bias_partial, g_bias);
-  return check_launch("wgrad_tf32x3_kernel");
+  return check_launch(F16 ? "wgrad_split3_kernel<fp16>" : "wgrad_split3_kernel<tf32>");
+}
+
+extern "C" MFLOW_API int mflow_conv2d_wgrad_tf32x3(const mflow_conv_desc* d, const float* x, const float* g_y, float* g_w,
+                                                   float* g_bias, void* workspace, void* stream) {
+  return launch_wgrad<false>(d, x, g_y, nullptr, nullptr, g_w, g_bias, workspace, stream);
+}
+
+extern "C" MFLOW_API int mflow_conv2d_wgrad_f16x3(const mflow_conv_desc* d, const float* x, const float* g_y, const float* x_amax,
+                                                  const float* g_amax, float* g_w, float* g_bias, void* workspace, void* stream) {
+  return launch_wgrad<true>(d, x, g_y, x_amax, g_amax, g_w, g_bias, workspace, stream);
 }

@@ -77,6 +77,9 @@ _SIGNATURES = {
     "mflow_rqs_box_backward": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 8),
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
     "mflow_conv2d_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
+    "mflow_conv2d_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 11),
+    "mflow_conv2d_wgrad_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
+    "mflow_absmax": (ctypes.c_int, [c_f32p, i64, c_f32p, c_f32p]),
     "mflow_conv2d_wgrad_workspace_bytes": (i64, [ctypes.POINTER(ConvDesc)]),
     "mflow_conv2d_wgrad_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 6),
     "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),

@@ -8,6 +8,9 @@ class _Config:
     conditioner_math = os.environ.get("MFLOW_CONDITIONER_MATH", "fp32")
     # image-conditioner convolutions on the tcgen05 tensor cores (3xTF32); False = cuDNN fp32 library calls
     conv_tensor_cores = os.environ.get("MFLOW_CONV_TC", "1") != "0"
+    # operand format of those kernels' error-compensated split: "fp16" (kind::f16, power-of-two operand scaling from the
+    # tensors' absolute maxima; twice the tensor-core rate) or "tf32" (kind::tf32, no scaling)
+    conv_operand_format = os.environ.get("MFLOW_CONV_FORMAT", "fp16")
     # weight gradients of those convolutions on the tensor cores too; False = cuDNN / cuBLAS fp32 library calls
     conv_wgrad_tensor_cores = os.environ.get("MFLOW_CONV_WGRAD_TC", "1") != "0"
     # smallest feature-map width that goes to the tensor-core weight-gradient kernel (4, 8, 16 or 32); below it the

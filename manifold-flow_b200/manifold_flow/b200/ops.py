@@ -253,6 +253,43 @@ def _split_weight(w_taps):
     return hi.contiguous(), lo.contiguous(), n_pad, k_pad
 
 
+def _split_weight_f16(w_taps):
+    """[taps, N, K] fp32 -> (hi, lo, unscale): fp16 halves of the weights scaled per output row n by the power of two that
+    puts the row's largest magnitude into [2^13, 2^14) (fp16 keeps 11 significant bits only inside its 5-bit exponent
+    range), zero padded to N % 128 == 0 and K % 32 == 0; unscale[n] = 2^-s_n is applied to the accumulator by the kernel's
+    epilogue.  hi + lo reproduces the scaled weight to ~2^-22 of the row maximum."""
+    taps, n, k = w_taps.shape
+    n_pad, k_pad = (n + 127) // 128 * 128, (k + 31) // 32 * 32
+    amax = w_taps.abs().amax(dim=(0, 2))
+    _, exp = torch.frexp(amax)                       # amax = m * 2^exp with m in [0.5, 1): floor(log2 amax) = exp - 1
+    shift = torch.where(amax > 0, 14 - exp, torch.zeros_like(exp)).clamp(-100, 100).to(torch.float32)
+    wt = torch.zeros(taps, n_pad, k_pad, dtype=torch.float32, device=w_taps.device)
+    wt[:, :n, :k] = w_taps * torch.exp2(shift)[None, :, None]
+    hi = wt.to(torch.float16)
+    lo = (wt - hi.to(torch.float32)).to(torch.float16)
+    unscale = torch.ones(n_pad, dtype=torch.float32, device=w_taps.device)
+    unscale[:n] = torch.exp2(-shift)
+    return hi.contiguous(), lo.contiguous(), unscale, n_pad, k_pad
+
+
+def tensor_amax(x, fresh=False):
+    """Device scalar holding max |x|: the operand scale of the fp16-split kernels.  Kernels of this library publish it with
+    their output (attribute ``_mflow_amax`` of the tensor they return: valid for exactly that tensor object at that
+    version); for any other tensor one ``mflow_absmax`` pass computes it (and remembers it on the tensor)."""
+    tag = getattr(x, "_mflow_amax", None)
+    if tag is not None and not fresh and tag[1] == x._version and tag[2] == x.data_ptr():
+        return tag[0]
+    out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    check(lib().mflow_absmax(ptr(x), x.numel(), ptr(out), stream()), "mflow_absmax")
+    cabi.count_launch()
+    x._mflow_amax = (out, x._version, x.data_ptr())
+    return out
+
+
+def _publish_amax(y, slot):
+    y._mflow_amax = (slot, y._version, y.data_ptr())
+
+
 class _WeightCache:
     """Split / padded operand copies of a convolution weight, rebuilt when the parameter changes.
     Entries are bound to the tensor object itself (weak reference), not just to its id(): Python reuses
@@ -261,11 +298,11 @@ class _WeightCache:
     def __init__(self):
         self._entries = {}
 
-    def get(self, weight, transposed, owner=None):
+    def get(self, weight, transposed, owner=None, fmt="tf32"):
         """owner: the long-lived tensor (parameter) that `weight` is a fresh view of, if any - the entry is then
         bound to the owner, so that a new view object per call does not miss."""
         anchor = weight if owner is None else owner
-        key = (id(anchor), transposed)
+        key = (id(anchor), transposed, fmt)
         ver = (weight.data_ptr(), anchor._version, tuple(weight.shape), config.cache_epoch)
         ent = self._entries.get(key)
         if ent is None or ent[0]() is not anchor or ent[1] != ver:
@@ -277,7 +314,7 @@ class _WeightCache:
                     taps = weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
                 else:  # data gradient: correlation with the taps flipped and channels swapped
                     taps = weight.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
-                ent = (weakref.ref(anchor), ver, _split_weight(taps))
+                ent = (weakref.ref(anchor), ver, _split_weight_f16(taps) if fmt == "fp16" else _split_weight(taps))
             self._entries[key] = ent
         return ent[2]
 
@@ -285,20 +322,39 @@ class _WeightCache:
 _weight_cache = _WeightCache()
 
 
-def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in):
-    hi, lo, n_pad, k_pad = split
+def _conv_format():
+    fmt = config.conv_operand_format
+    if fmt not in ("fp16", "tf32"):
+        raise ValueError("config.conv_operand_format must be 'fp16' or 'tf32', got {!r}".format(fmt))
+    return fmt
+
+
+def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in, x_amax=None):
+    """One convolution launch.  fp16 format: ``x_amax`` is the device scalar max |x| (``tensor_amax``); the launch publishes
+    max |y| on the returned tensor for the next consumer."""
+    f16 = len(split) == 5
     b, c_in, h, w = x.shape
+    n_pad, k_pad = split[-2], split[-1]
     d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0,
                  n_pad=n_pad, k_pad=k_pad)
     y = torch.empty((b, c_out, h, w), dtype=torch.float32, device=x.device)
+    out_amax = torch.zeros(1, dtype=torch.float32, device=x.device) if f16 else None
     tok = None
-    if cabi.kernel_timer:  # useful (fp32-equivalent) FLOPs: 2 * pixels * c_in * c_out * taps - NOT the three TF32 passes
+    if cabi.kernel_timer:  # useful (fp32-equivalent) FLOPs: 2 * pixels * c_in * c_out * taps - NOT the three tensor passes
         tok = cabi.kernel_timer.begin(f"conv{kernel}x{kernel}[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out * kernel * kernel)
-    check(lib().mflow_conv2d_tf32x3(ctypes.byref(d), ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(residual), ptr(gate), ptr(y), stream()),
-          "mflow_conv2d_tf32x3")
+    if f16:
+        hi, lo, unscale = split[0], split[1], split[2]
+        check(lib().mflow_conv2d_f16x3(ctypes.byref(d), ptr(x), ptr(hi), ptr(lo), ptr(unscale), ptr(x_amax), ptr(bias), ptr(residual),
+                                       ptr(gate), ptr(y), ptr(out_amax), stream()), "mflow_conv2d_f16x3")
+    else:
+        hi, lo = split[0], split[1]
+        check(lib().mflow_conv2d_tf32x3(ctypes.byref(d), ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(residual), ptr(gate), ptr(y), stream()),
+              "mflow_conv2d_tf32x3")
     if tok:
         cabi.kernel_timer.end(tok)
     cabi.count_launch()
+    if f16:
+        _publish_amax(y, out_amax)
     return y
 
 
@@ -307,11 +363,16 @@ def conv_wgrad_supported(x, c_out, kernel):
     return h == w and w in (4, 8, 16, 32) and w >= config.conv_wgrad_min_width and b >= 1 and (kernel == 1 or c_out <= 112)
 
 
-def conv_wgrad_tc(g, x, kernel, relu_in, with_bias=False):
-    """g_w[co, ci, ky, kx] of y = conv2d(relu?(x), W): pixels-as-K GEMM on the tensor cores (3xTF32), deterministic.
+def conv_wgrad_tc(g, x, kernel, relu_in, with_bias=False, x_amax=None, g_amax=None):
+    """g_w[co, ci, ky, kx] of y = conv2d(relu?(x), W): pixels-as-K GEMM on the tensor cores (error-compensated split of
+    both operands, fp16 or TF32 format), deterministic.
     with_bias: also return the bias gradient sum_{b,h,w} g (computed inside the same kernel) as (g_w, g_b)."""
     require_cuda(g, x)
     g, x = _c(g), _c(x)
+    f16 = _conv_format() == "fp16"
+    if f16:
+        x_amax = tensor_amax(x) if x_amax is None else x_amax
+        g_amax = tensor_amax(g) if g_amax is None else g_amax
     b, c_in, h, w = x.shape
     c_out = g.shape[1]
     d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0, n_pad=0, k_pad=0)
@@ -321,7 +382,11 @@ def conv_wgrad_tc(g, x, kernel, relu_in, with_bias=False):
     tok = None
     if cabi.kernel_timer:
         tok = cabi.kernel_timer.begin(f"wgrad{kernel}x{kernel}[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out * kernel * kernel)
-    check(lib().mflow_conv2d_wgrad_tf32x3(ctypes.byref(d), ptr(x), ptr(g), ptr(gw), ptr(gb), ptr(ws), stream()), "mflow_conv2d_wgrad_tf32x3")
+    if f16:
+        check(lib().mflow_conv2d_wgrad_f16x3(ctypes.byref(d), ptr(x), ptr(g), ptr(x_amax), ptr(g_amax), ptr(gw), ptr(gb), ptr(ws), stream()),
+              "mflow_conv2d_wgrad_f16x3")
+    else:
+        check(lib().mflow_conv2d_wgrad_tf32x3(ctypes.byref(d), ptr(x), ptr(g), ptr(gw), ptr(gb), ptr(ws), stream()), "mflow_conv2d_wgrad_tf32x3")
     if tok:
         cabi.kernel_timer.end(tok)
     cabi.count_launch(2)
@@ -339,8 +404,10 @@ class _ConvTC(torch.autograd.Function):
         x = _c(x)
         residual = None if residual is None else _c(residual)
         kernel = weight.shape[2]
-        y = _conv_tc_launch(x, _weight_cache.get(weight, False, owner), weight.shape[0], kernel, bias, residual, None, relu_in)
-        ctx.owner = owner
+        fmt = _conv_format()
+        x_amax = tensor_amax(x) if fmt == "fp16" else None
+        y = _conv_tc_launch(x, _weight_cache.get(weight, False, owner, fmt), weight.shape[0], kernel, bias, residual, None, relu_in, x_amax)
+        ctx.owner, ctx.fmt, ctx.x_amax = owner, fmt, x_amax
         ctx.save_for_backward(x, weight)
         ctx.relu_in, ctx.has_bias, ctx.has_res = relu_in, bias is not None, residual is not None
         return y
@@ -351,14 +418,16 @@ class _ConvTC(torch.autograd.Function):
         g = _c(g)
         gx = gw = gb = None
         kernel = weight.shape[2]
+        g_amax = tensor_amax(g) if ctx.fmt == "fp16" else None   # one scale for the data and the weight gradient
         if ctx.needs_input_grad[0]:
-            gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner), weight.shape[1], kernel, None, None, x if ctx.relu_in else None, False)
+            gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner, ctx.fmt), weight.shape[1], kernel, None, None,
+                                 x if ctx.relu_in else None, False, g_amax)
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
             if want_bias:   # the weight-gradient kernel sums g over the pixels on the side
-                gw, gb = conv_wgrad_tc(g, x, kernel, ctx.relu_in, with_bias=True)
+                gw, gb = conv_wgrad_tc(g, x, kernel, ctx.relu_in, with_bias=True, x_amax=ctx.x_amax, g_amax=g_amax)
             else:
-                gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in)
+                gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in, x_amax=ctx.x_amax, g_amax=g_amax)
         elif ctx.needs_input_grad[1]:   # shapes the tensor-core kernel does not take (4x4 maps): library call
             xin = torch.relu(x) if ctx.relu_in else x
             gw = torch.ops.aten.convolution_backward(g, xin, weight, None, [1, 1], [kernel // 2] * 2, [1, 1], False, [0, 0], 1,
