@@ -97,7 +97,9 @@ struct Ring {
   __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 
-template <bool F16>
+// CS: compile-time number of floats between two channels of the raw box (box_w * box_h; 0 = read it from the
+// arguments): the gather's 32 shared-memory loads then use immediate offsets instead of one address multiply each.
+template <bool F16, int CS>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_whi8,
@@ -195,7 +197,8 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (!ahead) load_raw(kb);
         else if (a.taps == 1 && kb + 1 < a.k_blocks) load_raw(kb + 1);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
-          if (ahead && a.taps > 1 && tap == 2 && kb + 1 < a.k_blocks) load_raw(kb + 1);
+          // (fp16 3x3: the transform warps pre-split box kb + 1 during the last taps of block kb, so it is requested earlier)
+          if (ahead && a.taps > 1 && tap == (F16 ? 1 : 2) && kb + 1 < a.k_blocks) load_raw(kb + 1);
           if (kb == 0 && tap < n_w_pre) continue;
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
           if (a.tail_k8 && kb == a.k_blocks - 1) {
@@ -274,7 +277,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int pm = quad * 32 + lane;
     const int pw = pm % a.W, pg = pm / a.W;
     const int phl = pg % a.rows_per_tile, pbl = pg / a.rows_per_tile;
-    const int chan_stride = a.box_h * a.box_w;                              // floats between channels in the raw box
+    const int chan_stride = CS ? CS : a.box_h * a.box_w;                    // floats between channels in the raw box
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     // The halves alternate pipeline steps (half h owns TMEM stage h): two steps are in flight in different
@@ -284,12 +287,53 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (F16) pow2_scale_from_amax(a.in_amax, sa, inv_sa);
     Ring rb(a.n_raw);
     int step = 0, pa = 0;   // step parity; phase of this half's stage
+    // fp16 3x3 ("pre-split"): every element of a raw box feeds nine taps, so ReLU, scaling and the hi / lo split are done
+    // ONCE per box, in place - the fp32 values of channels (2p, 2p + 1) at a pixel are replaced by the packed hi pair and
+    // the packed lo pair - and a tap step is just 32 loads and 4 tensor-memory stores (splitting inside every tap step
+    // made the kernel instruction-issue bound: 69% of the issue slots at 50% tensor-pipe activity, ncu).  With two raw
+    // slots the eight warps split box kb + 1 in slices during taps kSplitTap0..8 of block kb.
+    const bool pre = F16 && a.taps == 9;
+    const bool overlap = pre && a.n_raw >= 2;
+    constexpr int kSplitTap0 = 4;
+    const int xf_tid = threadIdx.x - 64;                                            // 0..255 over the eight transform warps
+    const int n_items = a.imgs_per_tile * (kBlockK / 2) * chan_stride;              // (channel pair, pixel) items of one box
+    const int per_thread = (n_items + 255) / 256, per_slice = (per_thread + (8 - kSplitTap0)) / (9 - kSplitTap0);
+    auto split_box = [&](uint8_t* boxp, int j0, int j1) {
+      float* box = reinterpret_cast<float*>(boxp);
+      for (int j = j0; j < j1; ++j) {
+        const int i = xf_tid + 256 * j;
+        if (i < n_items) {
+          const int p = i / chan_stride, q = i - p * chan_stride;
+          float* e = box + 2 * p * chan_stride + q;
+          float v0 = e[0], v1 = e[chan_stride];
+          if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          uint32_t hi, lo;
+          split_f16x2(v0 * sa, v1 * sa, hi, lo);
+          e[0] = __uint_as_float(hi);
+          e[chan_stride] = __uint_as_float(lo);
+        }
+      }
+    };
     for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
       const int nch = F16 ? (min(kBlockK, a.Cin - kb * kBlockK) + 15) & ~15
                           : (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
-      mbar_wait(&raw_full[rb.slot], rb.phase);
+      if (!pre) {
+        mbar_wait(&raw_full[rb.slot], rb.phase);
+      } else {
+        if (kb == 0 || !overlap) {
+          mbar_wait(&raw_full[rb.slot], rb.phase);
+          split_box(s_raw + rb.slot * a.raw_bytes, 0, per_thread);
+        }
+        named_bar_sync<3>(kXfWarps * 32);   // this block's box is split completely (all eight warps took part)
+      }
       const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
+        if (overlap && tap >= kSplitTap0 && kb + 1 < a.k_blocks) {   // every warp, whichever half owns this step
+          const int ns = rb.slot + 1 == rb.n ? 0 : rb.slot + 1;
+          if (tap == kSplitTap0) mbar_wait(&raw_full[ns], ns == 0 ? rb.phase ^ 1 : rb.phase);
+          const int j0 = (tap - kSplitTap0) * per_slice;
+          split_box(s_raw + ns * a.raw_bytes, j0, min(per_thread, j0 + per_slice));
+        }
         if (step != half) continue;
         const float* src = raw + (pad ? (tap / 3) * a.box_w + tap % 3 + 3 : 0);
         mbar_wait(&a_empty[half], pa ^ 1);
@@ -297,7 +341,23 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc_fence_after();
         // gather the pixel's channels of the tap, optional ReLU, hi / lo split, and store both parts into the
         // pixel's TMEM lane (A_hi in the first kAPart columns of the stage, A_lo in the next kAPart)
-        if (F16) {
+        if (F16 && pre) {
+          const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {     // 16 channels = 8 packed hi words + 8 packed lo words of the pre-split box
+            const int c0 = g * 16;
+            if (c0 < nch) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                hi[c] = srcw[(c0 + 2 * c) * chan_stride];
+                lo[c] = srcw[(c0 + 2 * c + 1) * chan_stride];
+              }
+              tmem_st_32x8u(t_a + g * 8, hi);
+              tmem_st_32x8u(t_a + kAPart + g * 8, lo);
+            }
+          }
+        } else if (F16) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {     // 16 channels = 8 columns of packed fp16 pairs per part
             const int c0 = g * 16;
@@ -505,14 +565,23 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   dim3 grid(n_tiles, (a.Cout + kTileN - 1) / kTileN);
   const size_t smem = (size_t)total(a.n_raw, a.n_b);
   // the opt-in shared-memory limit is a per-device function attribute
-  static size_t attr_smem[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && smem > attr_smem[dev]) {
-    cudaFuncSetAttribute(conv_split3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_cta_budget);
-    attr_smem[dev] = one_cta_budget;
-  }
-  conv_split3_kernel<F16><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a);
+#define MFLOW_CONV_LAUNCH(CS_)                                                                                             \
+  do {                                                                                                                     \
+    static bool attr_set[64] = {};   /* the opt-in shared-memory limit is a per-device function attribute */               \
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {                                                                          \
+      cudaFuncSetAttribute(conv_split3_kernel<F16, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_cta_budget); \
+      attr_set[dev] = true;                                                                                                \
+    }                                                                                                                      \
+    conv_split3_kernel<F16, CS_><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a); \
+  } while (0)
+  const int cs = a.box_w * a.box_h;
+  if (F16 && cs == 240) MFLOW_CONV_LAUNCH(240);        // 3x3 on 32x32 and 16x16 maps
+  else if (F16 && cs == 160) MFLOW_CONV_LAUNCH(160);   // 3x3 on 8x8 maps
+  else if (F16 && cs == 128) MFLOW_CONV_LAUNCH(128);   // 1x1
+  else MFLOW_CONV_LAUNCH(0);
+#undef MFLOW_CONV_LAUNCH
   return check_launch(F16 ? "conv_split3_kernel<fp16>" : "conv_split3_kernel<tf32>");
 }
 
