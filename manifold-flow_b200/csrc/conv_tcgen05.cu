@@ -51,8 +51,8 @@ constexpr int kBlockK = 32;   // input channels per pipeline step
 constexpr int kStageBytes = kTileM * kBlockK * 4;  // 16 KB: one 32-channel chunk of the output / aux tile (fp32) in the staging area
 constexpr int kConvThreads = 320;   // 2 control warps + 8 transform / epilogue warps
 constexpr int kXfWarps = 8;
-constexpr int kStagesA = 2;       // activation operand stages in TMEM
-constexpr int kTmemCols = 256;    // 128 accumulator columns + kStagesA x (A_hi + A_lo): 32 + 32 columns (TF32) or 16 + 16 (fp16 pairs)
+constexpr int kMaxStagesA = 4;    // activation operand stages in TMEM: 2 (TF32: 64 columns each) or 4 (fp16: 32 columns each)
+constexpr int kTmemCols = 256;    // 128 accumulator columns + stages x (A_hi + A_lo): 2 x (32 + 32) columns (TF32) or 4 x (16 + 16) (fp16 pairs)
 constexpr int kMaxStagesB = 4;
 constexpr int kMaxRaw = 2;
 
@@ -118,9 +118,9 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* raw_empty = raw_full + kMaxRaw;          // [kMaxRaw]
   uint64_t* b_full = raw_empty + kMaxRaw;            // [kMaxStagesB]
   uint64_t* b_empty = b_full + kMaxStagesB;          // [kMaxStagesB]
-  uint64_t* a_full = b_empty + kMaxStagesB;          // [kStagesA]
-  uint64_t* a_empty = a_full + kStagesA;             // [kStagesA]
-  uint64_t* acc_full_p = a_empty + kStagesA;
+  uint64_t* a_full = b_empty + kMaxStagesB;          // [kMaxStagesA]
+  uint64_t* a_empty = a_full + kMaxStagesA;          // [kMaxStagesA]
+  uint64_t* acc_full_p = a_empty + kMaxStagesA;
   uint64_t* aux_full_p = acc_full_p + 1;
   uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(aux_full_p + 1);
 #define acc_full (*acc_full_p)
@@ -129,6 +129,10 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kAPart = F16 ? kBlockK / 2 : kBlockK;   // TMEM columns of one part (hi or lo) of an activation stage
+  // fp16 stages are half as wide, so four fit: each half of the transform warps owns two and can run one step ahead of
+  // the MMAs that read its previous stage (with one stage per half it idled for the whole MMA + commit latency: 20% of
+  // all warp samples in ncu were that wait)
+  constexpr int kStagesA = F16 ? 4 : 2;
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * kTileN;
   const int tiles_per_img = a.imgs_per_tile > 1 ? 1 : a.H / a.rows_per_tile;
@@ -142,7 +146,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     prefetch_tensormap(&map_wlo);
     for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kXfWarps); }
     for (int i = 0; i < kMaxStagesB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < kStagesA; ++i) { mbar_init(&a_full[i], kXfWarps / 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kMaxStagesA; ++i) { mbar_init(&a_full[i], kXfWarps / 2); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_init(&aux_full, 1);
     fence_barrier_init();
@@ -280,13 +284,14 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int chan_stride = CS ? CS : a.box_h * a.box_w;                    // floats between channels in the raw box
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    // The halves alternate pipeline steps (half h owns TMEM stage h): two steps are in flight in different
-    // warps, so one warp's gather / split / tcgen05.st latency hides behind the other's.
-    const uint32_t t_a = t_lane + kTileN + half * 2 * kAPart;
+    // The halves alternate pipeline steps (half h owns the TMEM stages h, h + 2, ...): two steps are in flight in
+    // different warps, so one warp's gather / split / tcgen05.st latency hides behind the other's.
+    int my_stage = 0;          // which of this half's stages the next step uses
+    uint32_t my_phase = 0;     // bit i: phase of this half's stage i
     float sa = 1.f, inv_sa = 1.f;   // fp16 path: power-of-two scale of the activation operand and its inverse
     if (F16) pow2_scale_from_amax(a.in_amax, sa, inv_sa);
     Ring rb(a.n_raw);
-    int step = 0, pa = 0;   // step parity; phase of this half's stage
+    int step = 0;   // step parity
     // fp16 3x3 ("pre-split"): every element of a raw box feeds nine taps, so ReLU, scaling and the hi / lo split are done
     // ONCE per box, in place - the fp32 values of channels (2p, 2p + 1) at a pixel are replaced by the packed hi pair and
     // the packed lo pair - and a tap step is just 32 loads and 4 tensor-memory stores (splitting inside every tap step
@@ -336,8 +341,10 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         if (step != half) continue;
         const float* src = raw + (pad ? (tap / 3) * a.box_w + tap % 3 + 3 : 0);
-        mbar_wait(&a_empty[half], pa ^ 1);
-        pa ^= 1;
+        const int stage = half + 2 * my_stage;
+        const uint32_t t_a = t_lane + kTileN + stage * 2 * kAPart;
+        mbar_wait(&a_empty[stage], ((my_phase >> my_stage) & 1u) ^ 1u);
+        my_phase ^= 1u << my_stage;
         tc_fence_after();
         // gather the pixel's channels of the tap, optional ReLU, hi / lo split, and store both parts into the
         // pixel's TMEM lane (A_hi in the first kAPart columns of the stage, A_lo in the next kAPart)
@@ -394,7 +401,8 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[half]);
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        if (kStagesA > 2) my_stage ^= 1;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rb.slot]);   // this warp's reads of the box are program-ordered before
@@ -451,7 +459,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #undef acc_full
 #undef aux_full
 #undef s_tmem
-constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kStagesA + 2) * 8 + 16;
+constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kMaxStagesA + 2) * 8 + 16;
 
 // ---- host side --------------------------------------------------------------------------------
 }  // namespace mflow
