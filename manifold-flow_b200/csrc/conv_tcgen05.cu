@@ -83,7 +83,15 @@ struct ConvArgs {
   const float* in_amax;   // device scalar: absolute maximum of x (null = no scaling: the caller vouches for the range)
   const float* w_unscale; // [n_pad] 2^-s_n undoing the per-output-channel weight scale
   float* out_amax;        // device scalar (zero-initialised by the caller) receiving max |y| of this launch, or null
+#ifdef MFLOW_CONV_ABLATE
+  int ablate;             // dev-only timing experiments (wrong results): 1 no B_lo product, 2 no gather loads, 4 MMA N = 64, 16 no TMEM stores
+#endif
 };
+#ifdef MFLOW_CONV_ABLATE
+#define MFLOW_ABL(bit) (a.ablate & (bit))
+#else
+#define MFLOW_ABL(bit) false
+#endif
 
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 // round to nearest TF32 (ties away): the tensor core truncates its fp32 inputs, so the low part of the
@@ -233,7 +241,8 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // elect.sync (not lane == 0): the compiler then issues the tcgen05 instructions back to back instead of
     // wrapping each one in a warp-election loop (the MMAs here are only 56 cycles long)
     if (elect_one()) {
-      const uint32_t idesc = F16 ? idesc_f16(kTileM, a.n_tile, 0, 0) : idesc_tf32(kTileM, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+      const int n_mma = MFLOW_ABL(4) ? 64 : a.n_tile;
+      const uint32_t idesc = F16 ? idesc_f16(kTileM, n_mma, 0, 0) : idesc_tf32(kTileM, n_mma, /*a K-major*/ 0, /*b K-major*/ 0);
       constexpr int kStepK = F16 ? 16 : 8;   // channels per MMA instruction: 32 bytes of a weight row, 8 TMEM columns of A
       Ring sb(a.n_b), sa(kStagesA);
       for (int kb = 0; kb < a.k_blocks; ++kb) {
@@ -256,7 +265,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             if (F16) {
               umma_f16_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
               umma_f16_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
-              umma_f16_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
+              if (!MFLOW_ABL(1)) umma_f16_ts(tmem, ahi + kk * 8, d_blo + 2 * kk, idesc, 1);
             } else {
               umma_tf32_ts(tmem, ahi + kk * 8, d_bhi + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
               umma_tf32_ts(tmem, alo + kk * 8, d_bhi + 2 * kk, idesc, 1);
@@ -357,11 +366,13 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                hi[c] = srcw[(c0 + 2 * c) * chan_stride];
-                lo[c] = srcw[(c0 + 2 * c + 1) * chan_stride];
+                hi[c] = MFLOW_ABL(2) ? (uint32_t)c : srcw[(c0 + 2 * c) * chan_stride];
+                lo[c] = MFLOW_ABL(2) ? (uint32_t)c : srcw[(c0 + 2 * c + 1) * chan_stride];
               }
-              tmem_st_32x8u(t_a + g * 8, hi);
-              tmem_st_32x8u(t_a + kAPart + g * 8, lo);
+              if (!MFLOW_ABL(16)) {
+                tmem_st_32x8u(t_a + g * 8, hi);
+                tmem_st_32x8u(t_a + kAPart + g * 8, lo);
+              }
             }
           }
         } else if (F16) {
@@ -487,6 +498,9 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   ConvArgs a{};
   a.y = y; a.bias = bias; a.residual = residual; a.gate = gate;
   a.in_amax = in_amax; a.w_unscale = w_unscale; a.out_amax = out_amax;
+#ifdef MFLOW_CONV_ABLATE
+  { const char* e = getenv("MFLOW_CONV_ABLATE"); a.ablate = e ? atoi(e) : 0; }
+#endif
   a.B = B; a.Cin = (int)d->c_in; a.Cout = (int)d->c_out; a.H = H; a.W = W;
   a.taps = d->kernel == 3 ? 9 : 1;
   a.relu_in = d->relu_in; a.relu_out = d->relu_out;
