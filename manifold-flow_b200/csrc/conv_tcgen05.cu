@@ -53,7 +53,7 @@ constexpr int kConvThreads = 320;   // 2 control warps + 8 transform / epilogue 
 constexpr int kXfWarps = 8;
 constexpr int kMaxStagesA = 4;    // activation operand stages in TMEM: 2 (TF32: 64 columns each) or 4 (fp16: 32 columns each)
 constexpr int kTmemCols = 256;    // 128 accumulator columns + stages x (A_hi + A_lo): 2 x (32 + 32) columns (TF32) or 4 x (16 + 16) (fp16 pairs)
-constexpr int kMaxStagesB = 4;
+constexpr int kMaxStagesB = 8;
 constexpr int kMaxRaw = 2;
 
 struct ConvArgs {
@@ -89,7 +89,17 @@ struct ConvArgs {
 };
 #ifdef MFLOW_CONV_ABLATE
 #define MFLOW_ABL(bit) (a.ablate & (bit))
+// dev-only per-CTA timeline: [cta][0] clock at entry, [1] after the set-up barrier, [2] first MMA issue, [3] accumulator
+// complete (seen by an epilogue warp), [4] epilogue done, [5] exit, [6] globaltimer at entry, [7] globaltimer at exit, [8] SM id
+__device__ long long g_conv_tl[4096][9];
+// ... and per-step stamps of CTA 600: [0] transform: before the stage wait, [1] stage free, [2] stage filled + arrived,
+// [3] MMA warp: activation stage full, [4] weights full, [5] MMAs issued + committed, [6] producer: weight slot free (TMA issue)
+__device__ long long g_conv_steps[7][64];
+#define MFLOW_ST(row, idx, cond) do { if (blockIdx.x == 600 && (cond) && (idx) < 64) g_conv_steps[row][idx] = clock64(); } while (0)
+#define MFLOW_TL(slot, cond) do { if ((cond) && blockIdx.x < 4096 && blockIdx.y == 0) g_conv_tl[blockIdx.x][slot] = clock64(); } while (0)
 #else
+#define MFLOW_ST(row, idx, cond) do { } while (0)
+#define MFLOW_TL(slot, cond) do { } while (0)
 #define MFLOW_ABL(bit) false
 #endif
 
@@ -131,11 +141,21 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* acc_full_p = a_empty + kMaxStagesA;
   uint64_t* aux_full_p = acc_full_p + 1;
   uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(aux_full_p + 1);
+  // per-output-channel epilogue constants of this CTA's 128 columns: weight unscale factor (1 on the TF32 path) and bias
+  float* s_fac = reinterpret_cast<float*>(s_tmem_p + 4);
+  float* s_bias = s_fac + kTileN;
 #define acc_full (*acc_full_p)
 #define aux_full (*aux_full_p)
 #define s_tmem (*s_tmem_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MFLOW_TL(0, threadIdx.x == 0);
+#ifdef MFLOW_CONV_ABLATE
+  if (threadIdx.x == 0 && blockIdx.x < 4096 && blockIdx.y == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_conv_tl[blockIdx.x][6] = (long long)t;
+    unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_conv_tl[blockIdx.x][8] = sm;
+  }
+#endif
   constexpr int kAPart = F16 ? kBlockK / 2 : kBlockK;   // TMEM columns of one part (hi or lo) of an activation stage
   // fp16 stages are half as wide, so four fit: each half of the transform warps owns two and can run one step ahead of
   // the MMAs that read its previous stage (with one stage per half it idled for the whole MMA + commit latency: 20% of
@@ -177,11 +197,17 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileN) {   // epilogue constants -> shared memory (dependent global loads
+    const int i = threadIdx.x - 64, co = n0 + i;          // inside the epilogue loop cost ~2500 cycles per 32-channel chunk)
+    s_fac[i] = F16 ? __ldg(a.w_unscale + co) : 1.f;       // w_unscale is padded like the weights
+    s_bias[i] = (a.bias != nullptr && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+  }
   if (warp == 1) tmem_alloc(&s_tmem, kTmemCols);  // [0,128) accumulator, then kStagesA x {A_hi, A_lo} x 32 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  MFLOW_TL(1, threadIdx.x == 0);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -209,10 +235,10 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (!ahead) load_raw(kb);
         else if (a.taps == 1 && kb + 1 < a.k_blocks) load_raw(kb + 1);
         for (int tap = 0; tap < a.taps; ++tap, sb.next()) {
-          // (fp16 3x3: the transform warps pre-split box kb + 1 during the last taps of block kb, so it is requested earlier)
-          if (ahead && a.taps > 1 && tap == (F16 ? 1 : 2) && kb + 1 < a.k_blocks) load_raw(kb + 1);
+          if (ahead && a.taps > 1 && tap == 2 && kb + 1 < a.k_blocks) load_raw(kb + 1);
           if (kb == 0 && tap < n_w_pre) continue;
           mbar_wait(&b_empty[sb.slot], sb.phase ^ 1);
+          MFLOW_ST(6, kb * a.taps + tap, true);
           if (a.tail_k8 && kb == a.k_blocks - 1) {
             // short last channel block (at most 8 TF32 / 16 fp16 channels): 32-byte rows (32B swizzle) instead of full
             // ones - the kernel is bound by the L2 -> shared weight traffic, and this block would be mostly zero padding
@@ -251,8 +277,11 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int tap = 0; tap < a.taps; ++tap, sb.next(), sa.next()) {
           const bool first = kb == 0 && tap == 0;
           mbar_wait(&a_full[sa.slot], sa.phase);
+          MFLOW_ST(3, kb * a.taps + tap, true);
           mbar_wait(&b_full[sb.slot], sb.phase);
+          MFLOW_ST(4, kb * a.taps + tap, true);
           tc_fence_after();
+          MFLOW_TL(2, first);
           const uint32_t ahi = tmem + kTileN + sa.slot * 2 * kAPart, alo = ahi + kAPart;
           const uint32_t bhi = smem_u32(s_b + sb.slot * 2 * a.w_tile_bytes);
           // K-major swizzled weight tiles (128-byte rows / 128B swizzle for TF32, 64-byte rows / 64B swizzle for fp16):
@@ -280,6 +309,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           }
           umma_commit(&a_empty[sa.slot]);  // slots are free again once these MMAs have read them
           umma_commit(&b_empty[sb.slot]);
+          MFLOW_ST(5, kb * a.taps + tap, true);
         }
       }
       umma_commit(&acc_full);
@@ -301,81 +331,24 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (F16) pow2_scale_from_amax(a.in_amax, sa, inv_sa);
     Ring rb(a.n_raw);
     int step = 0;   // step parity
-    // fp16 3x3 ("pre-split"): every element of a raw box feeds nine taps, so ReLU, scaling and the hi / lo split are done
-    // ONCE per box, in place - the fp32 values of channels (2p, 2p + 1) at a pixel are replaced by the packed hi pair and
-    // the packed lo pair - and a tap step is just 32 loads and 4 tensor-memory stores (splitting inside every tap step
-    // made the kernel instruction-issue bound: 69% of the issue slots at 50% tensor-pipe activity, ncu).  With two raw
-    // slots the eight warps split box kb + 1 in slices during taps kSplitTap0..8 of block kb.
-    const bool pre = F16 && a.taps == 9;
-    const bool overlap = pre && a.n_raw >= 2;
-    constexpr int kSplitTap0 = 4;
-    const int xf_tid = threadIdx.x - 64;                                            // 0..255 over the eight transform warps
-    const int n_items = a.imgs_per_tile * (kBlockK / 2) * chan_stride;              // (channel pair, pixel) items of one box
-    const int per_thread = (n_items + 255) / 256, per_slice = (per_thread + (8 - kSplitTap0)) / (9 - kSplitTap0);
-    auto split_box = [&](uint8_t* boxp, int j0, int j1) {
-      float* box = reinterpret_cast<float*>(boxp);
-      for (int j = j0; j < j1; ++j) {
-        const int i = xf_tid + 256 * j;
-        if (i < n_items) {
-          const int p = i / chan_stride, q = i - p * chan_stride;
-          float* e = box + 2 * p * chan_stride + q;
-          float v0 = e[0], v1 = e[chan_stride];
-          if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-          uint32_t hi, lo;
-          split_f16x2(v0 * sa, v1 * sa, hi, lo);
-          e[0] = __uint_as_float(hi);
-          e[chan_stride] = __uint_as_float(lo);
-        }
-      }
-    };
     for (int kb = 0; kb < a.k_blocks; ++kb, rb.next()) {
       const int nch = F16 ? (min(kBlockK, a.Cin - kb * kBlockK) + 15) & ~15
                           : (min(kBlockK, a.Cin - kb * kBlockK) + 7) & ~7;  // channels the MMAs of this block read
-      if (!pre) {
-        mbar_wait(&raw_full[rb.slot], rb.phase);
-      } else {
-        if (kb == 0 || !overlap) {
-          mbar_wait(&raw_full[rb.slot], rb.phase);
-          split_box(s_raw + rb.slot * a.raw_bytes, 0, per_thread);
-        }
-        named_bar_sync<3>(kXfWarps * 32);   // this block's box is split completely (all eight warps took part)
-      }
+      mbar_wait(&raw_full[rb.slot], rb.phase);
       const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
-        if (overlap && tap >= kSplitTap0 && kb + 1 < a.k_blocks) {   // every warp, whichever half owns this step
-          const int ns = rb.slot + 1 == rb.n ? 0 : rb.slot + 1;
-          if (tap == kSplitTap0) mbar_wait(&raw_full[ns], ns == 0 ? rb.phase ^ 1 : rb.phase);
-          const int j0 = (tap - kSplitTap0) * per_slice;
-          split_box(s_raw + ns * a.raw_bytes, j0, min(per_thread, j0 + per_slice));
-        }
         if (step != half) continue;
         const float* src = raw + (pad ? (tap / 3) * a.box_w + tap % 3 + 3 : 0);
         const int stage = half + 2 * my_stage;
         const uint32_t t_a = t_lane + kTileN + stage * 2 * kAPart;
+        MFLOW_ST(0, kb * a.taps + tap, quad == 0 && lane == 0);
         mbar_wait(&a_empty[stage], ((my_phase >> my_stage) & 1u) ^ 1u);
+        MFLOW_ST(1, kb * a.taps + tap, quad == 0 && lane == 0);
         my_phase ^= 1u << my_stage;
         tc_fence_after();
         // gather the pixel's channels of the tap, optional ReLU, hi / lo split, and store both parts into the
         // pixel's TMEM lane (A_hi in the first kAPart columns of the stage, A_lo in the next kAPart)
-        if (F16 && pre) {
-          const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {     // 16 channels = 8 packed hi words + 8 packed lo words of the pre-split box
-            const int c0 = g * 16;
-            if (c0 < nch) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                hi[c] = MFLOW_ABL(2) ? (uint32_t)c : srcw[(c0 + 2 * c) * chan_stride];
-                lo[c] = MFLOW_ABL(2) ? (uint32_t)c : srcw[(c0 + 2 * c + 1) * chan_stride];
-              }
-              if (!MFLOW_ABL(16)) {
-                tmem_st_32x8u(t_a + g * 8, hi);
-                tmem_st_32x8u(t_a + kAPart + g * 8, lo);
-              }
-            }
-          }
-        } else if (F16) {
+        if (F16) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {     // 16 channels = 8 columns of packed fp16 pairs per part
             const int c0 = g * 16;
@@ -383,7 +356,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                float v0 = src[(c0 + 2 * c) * chan_stride], v1 = src[(c0 + 2 * c + 1) * chan_stride];
+                float v0 = MFLOW_ABL(2) ? 1.f : src[(c0 + 2 * c) * chan_stride], v1 = MFLOW_ABL(2) ? 2.f : src[(c0 + 2 * c + 1) * chan_stride];
                 if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                 split_f16x2(v0 * sa, v1 * sa, hi[c], lo[c]);
               }
@@ -413,6 +386,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[stage]);
+        MFLOW_ST(2, kb * a.taps + tap, quad == 0 && lane == 0);
         if (kStagesA > 2) my_stage ^= 1;
       }
       __syncwarp();
@@ -421,6 +395,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    MFLOW_TL(3, warp == 2 && lane == 0);
     // aux tile in shared memory: layout [chunk][image][channel 32][row][w] (the TMA boxes), thread = pixel
     const int tile_px = a.rows_per_tile * a.W;
     float* stage = reinterpret_cast<float*>(s_b) + pbl * 32 * tile_px + phl * a.W + pw;
@@ -438,9 +413,8 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int co = n0 + c0 + j;
-        // fp16 path: undo the operand scales (exact powers of two); w_unscale is padded like the weights
-        float r = F16 ? v[j] * (inv_sa * __ldg(a.w_unscale + co)) : v[j];
-        r += (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+        // fp16 path: undo the operand scales (exact powers of two)
+        float r = F16 ? fmaf(v[j], inv_sa * s_fac[c0 + j], s_bias[c0 + j]) : v[j] + s_bias[c0 + j];
         if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
         if (a.relu_out) r = fmaxf(r, 0.f);
         if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
@@ -461,21 +435,40 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const uint32_t m = __reduce_max_sync(0xffffffffu, in_range ? __float_as_uint(out_max) : 0u);
       if (lane == 0) amax_publish(a.out_amax, __uint_as_float(m));
     }
-    if (issuer) tma_store_wait<0>();  // shared memory must stay valid until the stores have read it
+    if (issuer) tma_store_wait_read<0>();  // shared memory must stay valid until the stores have read it
+    MFLOW_TL(4, warp == 2 && lane == 0);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+  MFLOW_TL(5, threadIdx.x == 32);
+#ifdef MFLOW_CONV_ABLATE
+  if (threadIdx.x == 32 && blockIdx.x < 4096 && blockIdx.y == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_conv_tl[blockIdx.x][7] = (long long)t;
+  }
+#endif
 }
 #undef acc_full
 #undef aux_full
 #undef s_tmem
-constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kMaxStagesA + 2) * 8 + 16;
+constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kMaxStagesA + 2) * 8 + 16 + 2 * kTileN * 4;
 
 // ---- host side --------------------------------------------------------------------------------
 }  // namespace mflow
 
 using namespace mflow;
+
+#ifdef MFLOW_CONV_ABLATE
+extern "C" MFLOW_API int mflow_debug_conv_timeline(long long* out, int n_ctas) {
+  return cudaMemcpyFromSymbol(out, mflow::g_conv_tl, sizeof(long long) * 9 * (n_ctas < 4096 ? n_ctas : 4096)) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+}
+#endif
+
+#ifdef MFLOW_CONV_ABLATE
+extern "C" MFLOW_API int mflow_debug_conv_steps(long long* out) {
+  return cudaMemcpyFromSymbol(out, mflow::g_conv_steps, sizeof(long long) * 7 * 64) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+}
+#endif
 
 // shared host side of both operand formats
 template <bool F16>
@@ -547,6 +540,10 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   }
   if (a.n_b > steps) a.n_b = steps;
   if (a.n_raw > a.k_blocks) a.n_raw = a.k_blocks;
+#ifdef MFLOW_CONV_ABLATE
+  { const char* e = getenv("MFLOW_CONV_NB"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxStagesB) a.n_b = atoi(e); }
+  { const char* e = getenv("MFLOW_CONV_NRAW"); if (e && atoi(e) >= 1 && atoi(e) <= kMaxRaw) a.n_raw = atoi(e); }
+#endif
   a.ring_bytes = rings(a.n_raw, a.n_b) - a.n_raw * a.raw_bytes;   // weight ring, padded when the staging tile needs more
   MFLOW_REQUIRE(total(a.n_raw, a.n_b) <= one_cta_budget, "tile does not fit in shared memory");
 
