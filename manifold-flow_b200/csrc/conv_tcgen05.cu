@@ -141,9 +141,6 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* acc_full_p = a_empty + kMaxStagesA;
   uint64_t* aux_full_p = acc_full_p + 1;
   uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(aux_full_p + 1);
-  // per-output-channel epilogue constants of this CTA's 128 columns: weight unscale factor (1 on the TF32 path) and bias
-  float* s_fac = reinterpret_cast<float*>(s_tmem_p + 4);
-  float* s_bias = s_fac + kTileN;
 #define acc_full (*acc_full_p)
 #define aux_full (*aux_full_p)
 #define s_tmem (*s_tmem_p)
@@ -196,11 +193,6 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tma_load_3d(dst + a.w_tile_bytes, t8 ? &map_wlo8 : &map_wlo, &b_full[tap], 0, n0, tap);
       }
     }
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kTileN) {   // epilogue constants -> shared memory (dependent global loads
-    const int i = threadIdx.x - 64, co = n0 + i;          // inside the epilogue loop cost ~2500 cycles per 32-channel chunk)
-    s_fac[i] = F16 ? __ldg(a.w_unscale + co) : 1.f;       // w_unscale is padded like the weights
-    s_bias[i] = (a.bias != nullptr && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
   }
   if (warp == 1) tmem_alloc(&s_tmem, kTmemCols);  // [0,128) accumulator, then kStagesA x {A_hi, A_lo} x 32 columns
   tc_fence_before();
@@ -393,6 +385,16 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (lane == 0) mbar_arrive(&raw_empty[rb.slot]);   // this warp's reads of the box are program-ordered before
     }
     // ===== epilogue: TMEM -> registers -> staging tile -> TMA store; bias / residual / ReLU / mask fused =====
+    // Per-output-channel constants of this half's two 32-column chunks, one channel per lane, fetched while the last MMAs
+    // run and broadcast by shuffles below (as dependent __ldg's inside the loop they cost ~2500 cycles per chunk):
+    // weight unscale factor x activation unscale (fp16 path; w_unscale is padded like the weights) and bias.
+    float fac_l[2], bias_l[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int co = n0 + half * 32 + 64 * q + lane;
+      fac_l[q] = F16 ? inv_sa * __ldg(a.w_unscale + co) : 1.f;
+      bias_l[q] = (a.bias != nullptr && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+    }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     MFLOW_TL(3, warp == 2 && lane == 0);
@@ -414,7 +416,8 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int j = 0; j < 32; ++j) {
         const int co = n0 + c0 + j;
         // fp16 path: undo the operand scales (exact powers of two)
-        float r = F16 ? fmaf(v[j], inv_sa * s_fac[c0 + j], s_bias[c0 + j]) : v[j] + s_bias[c0 + j];
+        const float bj = __shfl_sync(0xffffffffu, c0 >= 64 ? bias_l[1] : bias_l[0], j);
+        float r = F16 ? fmaf(v[j], __shfl_sync(0xffffffffu, c0 >= 64 ? fac_l[1] : fac_l[0], j), bj) : v[j] + bj;
         if (a.aux_mode == 1) r += auxc[j * tile_px];                        // residual add
         if (a.relu_out) r = fmaxf(r, 0.f);
         if (a.aux_mode == 2) r = auxc[j * tile_px] > 0.f ? r : 0.f;         // ReLU mask of the backward pass
@@ -451,7 +454,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #undef acc_full
 #undef aux_full
 #undef s_tmem
-constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kMaxStagesA + 2) * 8 + 16 + 2 * kTileN * 4;
+constexpr int kConvBarrierBytes = (2 * kMaxRaw + 2 * kMaxStagesB + 2 * kMaxStagesA + 2) * 8 + 16;
 
 // ---- host side --------------------------------------------------------------------------------
 }  // namespace mflow
@@ -521,7 +524,8 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   // and within it a second raw box before a third weight stage: a single raw box costs ~5000 idle cycles at every
   // 32-channel block boundary (measured with the step trace), the weight tiles arrive in ~700.  Else one CTA per SM
   // with both rings deep.  The epilogue stages its output / aux tile over the drained rings.
-  const int two_cta_budget = 114 * 1024 - 512, one_cta_budget = 226 * 1024;
+  // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
+  const int two_cta_budget = 228 * 1024 / 2 - 1024, one_cta_budget = 226 * 1024;
   const int steps = a.k_blocks * a.taps;
   // bytes of the two rings; never less than the epilogue's staging tile, which is laid over them
   auto rings = [&](int n_raw, int n_b) {

@@ -25,8 +25,10 @@
 // * Split-K: CTA (ks, dy) reduces its share of the pixel blocks for the three taps of kernel row dy into
 //   three TMEM accumulators and writes a partial [tap][ci][co]; a second kernel adds the partials in index
 //   order (deterministic) and writes g_w in the reference's [co][ci][ky][kx] layout.
-// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 P transform (two sets of four alternate
-//   pixel blocks, one TMEM stage each) and epilogue, warps 10-13 Q split.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-13 P transform (three sets of four warps, one TMEM
+//   stage each: set s takes the (block, tap) work items s, s + 3, ... - for a 3x3 kernel that is always tap s, so a
+//   set has a whole block's MMA time for one transform; with two sets the kernel was bound by the transform
+//   latency, 2.5x off the tensor time) and epilogue, warps 14-17 Q split.
 #include <stdlib.h>
 
 #include "mflow_common.cuh"
@@ -37,7 +39,8 @@ namespace mflow {
 
 using namespace ptx;
 
-constexpr int kWgThreads = 32 * 14;
+constexpr int kWgThreads = 32 * 18;
+constexpr int kWgMaxSets = 3;                   // P transform sets = P stages in tensor memory: 3 (fp16: 32 columns each) or 2 (TF32: 64 each)
 constexpr int kWgBlockPx = 32;                 // pixels per K block
 constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
 constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
@@ -82,7 +85,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint8_t* s_q = smem;                                   // kWgQSlots x {Q_hi 16 KB, Q_lo 16 KB}
   uint8_t* s_p = s_q + kWgQSlots * 2 * kWgQBytes;        // kWgRawSlots x raw activation box
   __shared__ __align__(8) uint64_t rawp_full[kWgRawSlots], rawp_empty[kWgRawSlots], qraw_full[kWgQSlots], q_full[kWgQSlots],
-      q_empty[kWgQSlots], p_full[2], p_empty[2], acc_full;
+      q_empty[kWgQSlots], p_full[kWgMaxSets], p_empty[kWgMaxSets], acc_full;
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,13 +99,14 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   constexpr int taps_here = kTaps == 9 ? 3 : 1;
   constexpr int pad = kTaps == 9 ? 1 : 0;
   constexpr int kPPart = F16 ? kWgPCols / 2 : kWgPCols;   // TMEM columns of one part (hi or lo) of a P stage
+  constexpr int kWgSets = F16 ? 3 : 2;                    // three TF32 stages would not fit beside three accumulators
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_g);
-    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], 8); }
+    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], 4 * kWgSets); }
     for (int i = 0; i < kWgQSlots; ++i) { mbar_init(&qraw_full[i], 1); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < kWgSets; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
     mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
@@ -168,15 +172,14 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
           }
           umma_commit(&p_empty[sp]);
-          sp ^= 1;
-          pp ^= (sp == 0);
+          if (++sp == kWgSets) { sp = 0; pp ^= 1; }
         }
         umma_commit(&q_empty[rq.slot]);
       }
       umma_commit(&acc_full);
     }
-  } else if (warp < 10) {
-    // ===== P transform: TMEM lane = input channel; set s (warps 2-5 / 6-9) handles the blocks of parity s =====
+  } else if (warp < 2 + 4 * kWgSets) {
+    // ===== P transform: TMEM lane = input channel; set s (warps 2-5 / 6-9 / 10-13) handles the work items s, s + 3, ... =====
     const int quad = warp & 3, set = (warp - 2) >> 2;
     const int ch = quad * 32 + lane;                          // channel within the p tile = TMEM lane
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
@@ -185,7 +188,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (F16) { pow2_scale_from_amax(a.x_amax, sx, inv_sx); pow2_scale_from_amax(a.g_amax, sg, inv_sg); }
 
     WgRing rp(a.n_raw);
-    int pp = 0, item = 0;   // phase of this set's stage; running (block, tap) work item: set s takes the items of parity s
+    int pp = 0, turn = 0;   // phase of this set's stage; owner (set) of the running (block, tap) work item
     constexpr bool kPad = kTaps == 9;
     constexpr int kImgs = kW == 4 ? 2 : 1;                       // images per 32-pixel block
     constexpr int kRows = kWgBlockPx / kW / kImgs, kBoxW = kPad ? kW + 8 : kW;   // rows per image in the block
@@ -195,8 +198,8 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       bool loaded = false;
       float raw[kRawVec * 4];
 #pragma unroll
-      for (int t = 0; t < taps_here; ++t, ++item) {
-        if ((item & 1) != set) continue;
+      for (int t = 0; t < taps_here; ++t, turn = (turn + 1 == kWgSets ? 0 : turn + 1)) {
+        if (turn != set) continue;
         if (!loaded) {
           // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
           mbar_wait(&rawp_full[rp.slot], rp.phase);
@@ -247,7 +250,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box (or never needed it)
     }
-    // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take alternate 32-column chunks =====
+    // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take every third 32-column chunk =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const int ci = p0 + ch;
@@ -257,7 +260,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int t = 0; t < taps_here; ++t) {
       const int tap = kTaps == 9 ? dy * 3 + t : 0;
       float* dst = a.partial + (((int64_t)ks * a.taps + tap) * a.Cin + ci) * a.Cout + q0;
-      for (int c = set; c < n_chunks; c += 2) {
+      for (int c = set; c < n_chunks; c += kWgSets) {
         float v[32];
         tmem_ld_32x32(tmem + t_lane + t * a.n_tile + c * 32, v);
         if (ci < a.Cin) {
@@ -267,11 +270,11 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
       }
     }
-  } else {
+  } else if (warp >= 2 + 4 * kWgMaxSets) {
     // ===== Q split: the TMA-loaded fp32 tile becomes its TF32 hi part in place, the lo part goes next to it =====
     // These threads see every element of g_y exactly once, so the kernel-row-1 CTA of input-channel tile 0 also
     // accumulates the bias gradient sum_pixels g_y[co] (a thread's float4 positions are the same in every block).
-    const int tid = threadIdx.x - 320;   // 0..127
+    const int tid = threadIdx.x - 32 * (2 + 4 * kWgMaxSets);   // 0..127
     WgRing rq(kWgQSlots);
     const int n_vec = a.n_tile * (kWgBlockPx / 4);   // float4s of the tile
     const bool do_bias = a.bias_partial != nullptr && dy == (kTaps == 9 ? 1 : 0) && p0 == 0;
@@ -438,7 +441,7 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
   { const int widest = a.Cout < 128 ? a.Cout : 128; a.n_tile = (widest + 15) / 16 * 16; }
   a.tmem_cols = 512;
   a.x_amax = x_amax; a.g_amax = g_amax;
-  MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + 4 * kWgPCols <= 512, "accumulators do not fit in tensor memory");
+  MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + (F16 ? 3 * kWgPCols : 4 * kWgPCols) <= 512, "accumulators do not fit in tensor memory");
   const int n_ks = wgrad_splits(d);
   a.bias_partial = g_bias ? a.partial + (int64_t)n_ks * a.taps * a.Cin * a.Cout : nullptr;
 
