@@ -68,6 +68,16 @@ struct WgradArgs {
 __device__ __forceinline__ float wg_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float wg_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
+#ifdef MFLOW_CONV_ABLATE
+// dev-only per-block stamps of CTA (ks = 70, dy = 1, tile 0): [0] producer: raw slot free, [1] producer: Q slot free,
+// [2] Q split: raw tile arrived, [3] Q split: done, [4] P set 0: raw box arrived, [5] MMA: Q ready, [6] MMA: block issued,
+// [7] P transform of tap 0 done
+__device__ long long g_wg_steps[8][64];
+#define MFLOW_WST(row, idx, cond) do { if (blockIdx.x == 70 && blockIdx.y == (gridDim.y > 1 ? 1 : 0) && blockIdx.z == 0 && (cond) && (idx) < 64) g_wg_steps[row][idx] = clock64(); } while (0)
+#else
+#define MFLOW_WST(row, idx, cond) do { } while (0)
+#endif
+
 struct WgRing {
   int slot, phase, n;
   __device__ __forceinline__ WgRing(int depth) : slot(0), phase(0), n(depth) {}
@@ -104,7 +114,10 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_g);
-    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], 4 * kWgSets); }
+    // a raw box is released by the warps that read it: every set for a 3x3 kernel (each block has three work items),
+    // the one set that owns the block for a 1x1 kernel (a set that skips a block must not arrive: skipping is not gated
+    // by the box's arrival, so it could arrive for a later round of the slot inside the current phase)
+    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], kTaps == 9 ? 4 * kWgSets : 4); }
     for (int i = 0; i < kWgQSlots; ++i) { mbar_init(&qraw_full[i], 1); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < kWgSets; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
     mbar_init(&acc_full, 1);
@@ -127,9 +140,11 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int b = kW == 4 ? 2 * blk : blk / a.blocks_per_img, r = kW == 4 ? 0 : blk - b * a.blocks_per_img;
         const int h0 = r * a.rows;
         mbar_wait(&rawp_empty[rp.slot], rp.phase ^ 1);
+        MFLOW_WST(0, i, true);
         mbar_expect_tx(&rawp_full[rp.slot], a.raw_bytes);
         tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], pad ? -4 : 0, h0 + (pad ? dy - 1 : 0), p0, b);
         mbar_wait(&q_empty[rq.slot], rq.phase ^ 1);
+        MFLOW_WST(1, i, true);
         mbar_expect_tx(&qraw_full[rq.slot], a.n_tile * kWgBlockPx * 4);
         tma_load_3d(s_q + rq.slot * 2 * kWgQBytes, &map_g, &qraw_full[rq.slot], r * kWgBlockPx, q0, b);   // 4x4: box {16 px, n_tile, 2 images}
       }
@@ -142,6 +157,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       int sp = 0, pp = 0;   // P stage and its phase; one stage per (block, tap) work item
       for (int i = 0; i < n_my; ++i, rq.next()) {
         mbar_wait(&q_full[rq.slot], rq.phase);
+        MFLOW_WST(5, i, true);
         const uint32_t qhi = smem_u32(s_q + rq.slot * 2 * kWgQBytes);
         // 8..32-wide maps: one K-major tile [n_tile][128 B], 128B swizzle.  4x4 maps: the TMA box {16 px, n_tile, 2 images}
         // lands as two tiles [n_tile][64 B] (64B swizzle), k-steps 0,1 in the first image's tile and 2,3 in the second's.
@@ -175,6 +191,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           if (++sp == kWgSets) { sp = 0; pp ^= 1; }
         }
         umma_commit(&q_empty[rq.slot]);
+        MFLOW_WST(6, i, true);
       }
       umma_commit(&acc_full);
     }
@@ -203,6 +220,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (!loaded) {
           // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
           mbar_wait(&rawp_full[rp.slot], rp.phase);
+          MFLOW_WST(4, i, set == 0 && quad == 0 && lane == 0);
           const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + ch * kImgVec;   // box [image][channel][row][w]
 #pragma unroll
           for (int j = 0; j < kRawVec; ++j) {
@@ -246,9 +264,10 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[set]);
+        MFLOW_WST(7, i, t == 0 && quad == 0 && lane == 0);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box (or never needed it)
+      if (lane == 0 && loaded) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box
     }
     // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take every third 32-column chunk =====
     mbar_wait(&acc_full, 0);
@@ -284,6 +303,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (F16) pow2_scale_from_amax(a.g_amax, sg, inv_sg);
     for (int i = 0; i < n_my; ++i, rq.next()) {
       mbar_wait(&qraw_full[rq.slot], rq.phase);
+      MFLOW_WST(2, i, tid == 0);
       float4* hi = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes);
       float4* lo = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes + kWgQBytes);
       uint8_t* f16_hi = s_q + rq.slot * 2 * kWgQBytes + kWgQHiOff;
@@ -324,6 +344,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full[rq.slot]);
+      MFLOW_WST(3, i, tid == 0);
       last_slot = rq.slot;
     }
     if (do_bias) {
@@ -412,6 +433,12 @@ extern "C" MFLOW_API int64_t mflow_conv2d_wgrad_workspace_bytes(const mflow_conv
   const int64_t taps = d->kernel == 3 ? 9 : 1;
   return (int64_t)wgrad_splits(d) * (taps * d->c_in * d->c_out + d->c_out) * (int64_t)sizeof(float);
 }
+
+#ifdef MFLOW_CONV_ABLATE
+extern "C" MFLOW_API int mflow_debug_wgrad_steps(long long* out) {
+  return cudaMemcpyFromSymbol(out, mflow::g_wg_steps, sizeof(long long) * 8 * 64) == cudaSuccess ? MFLOW_OK : MFLOW_E_LAUNCH;
+}
+#endif
 
 template <bool F16>
 static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g_y, const float* x_amax, const float* g_amax,
