@@ -25,10 +25,12 @@
 // * Split-K: CTA (ks, dy) reduces its share of the pixel blocks for the three taps of kernel row dy into
 //   three TMEM accumulators and writes a partial [tap][ci][co]; a second kernel adds the partials in index
 //   order (deterministic) and writes g_w in the reference's [co][ci][ky][kx] layout.
-// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-13 P transform (three sets of four warps, one TMEM
-//   stage each: set s takes the (block, tap) work items s, s + 3, ... - for a 3x3 kernel that is always tap s, so a
-//   set has a whole block's MMA time for one transform; with two sets the kernel was bound by the transform
-//   latency, 2.5x off the tensor time) and epilogue, warps 14-17 Q split.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 P transform (two sets of four warps) and epilogue,
+//   warps 10-13 Q split.  fp16 path: a set owns every other pixel BLOCK, converts the block's pixels (halo included)
+//   ONCE - each becomes one register {fp16 hi, fp16 lo} - and assembles the three horizontally shifted windows with one
+//   byte-permute per pixel pair into a ring of five tensor-memory stages (one per (block, tap) work item).  Splitting
+//   inside every (block, tap) item made the kernel instruction-issue bound: 2250 cycles per block against 1008 of MMAs
+//   (per-block trace, tools/wgrad_trace.py).  TF32 path: the sets alternate work items, one stage each.
 #include <stdlib.h>
 
 #include "mflow_common.cuh"
@@ -39,8 +41,8 @@ namespace mflow {
 
 using namespace ptx;
 
-constexpr int kWgThreads = 32 * 18;
-constexpr int kWgMaxSets = 3;                   // P transform sets = P stages in tensor memory: 3 (fp16: 32 columns each) or 2 (TF32: 64 each)
+constexpr int kWgThreads = 32 * 14;
+constexpr int kWgMaxPStages = 5;                // P stages in tensor memory: 5 (fp16: 32 columns each) or 2 (TF32: 64 each)
 constexpr int kWgBlockPx = 32;                 // pixels per K block
 constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
 constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
@@ -69,11 +71,11 @@ __device__ __forceinline__ float wg_trunc(float v) { return __uint_as_float(__fl
 __device__ __forceinline__ float wg_round(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 #ifdef MFLOW_CONV_ABLATE
-// dev-only per-block stamps of CTA (ks = 70, dy = 1, tile 0): [0] producer: raw slot free, [1] producer: Q slot free,
+// dev-only per-block stamps of CTA (ks = 20, dy = 1, tile 0): [0] producer: raw slot free, [1] producer: Q slot free,
 // [2] Q split: raw tile arrived, [3] Q split: done, [4] P set 0: raw box arrived, [5] MMA: Q ready, [6] MMA: block issued,
 // [7] P transform of tap 0 done
 __device__ long long g_wg_steps[8][64];
-#define MFLOW_WST(row, idx, cond) do { if (blockIdx.x == 70 && blockIdx.y == (gridDim.y > 1 ? 1 : 0) && blockIdx.z == 0 && (cond) && (idx) < 64) g_wg_steps[row][idx] = clock64(); } while (0)
+#define MFLOW_WST(row, idx, cond) do { if (blockIdx.x == 20 && blockIdx.y == (gridDim.y > 1 ? 1 : 0) && blockIdx.z == 0 && (cond) && (idx) < 64) g_wg_steps[row][idx] = clock64(); } while (0)
 #else
 #define MFLOW_WST(row, idx, cond) do { } while (0)
 #endif
@@ -95,7 +97,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint8_t* s_q = smem;                                   // kWgQSlots x {Q_hi 16 KB, Q_lo 16 KB}
   uint8_t* s_p = s_q + kWgQSlots * 2 * kWgQBytes;        // kWgRawSlots x raw activation box
   __shared__ __align__(8) uint64_t rawp_full[kWgRawSlots], rawp_empty[kWgRawSlots], qraw_full[kWgQSlots], q_full[kWgQSlots],
-      q_empty[kWgQSlots], p_full[kWgMaxSets], p_empty[kWgMaxSets], acc_full;
+      q_empty[kWgQSlots], p_full[kWgMaxPStages], p_empty[kWgMaxPStages], acc_full;
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,17 +111,17 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   constexpr int taps_here = kTaps == 9 ? 3 : 1;
   constexpr int pad = kTaps == 9 ? 1 : 0;
   constexpr int kPPart = F16 ? kWgPCols / 2 : kWgPCols;   // TMEM columns of one part (hi or lo) of a P stage
-  constexpr int kWgSets = F16 ? 3 : 2;                    // three TF32 stages would not fit beside three accumulators
+  constexpr int kPStages = F16 ? 5 : 2;                   // all that fits beside three accumulators of <= 112 columns
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_g);
-    // a raw box is released by the warps that read it: every set for a 3x3 kernel (each block has three work items),
-    // the one set that owns the block for a 1x1 kernel (a set that skips a block must not arrive: skipping is not gated
-    // by the box's arrival, so it could arrive for a later round of the slot inside the current phase)
-    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], kTaps == 9 ? 4 * kWgSets : 4); }
+    // a raw box is released by the warps that read it: one set (fp16: it owns the block; TF32 1x1: it owns the block's
+    // only work item) or both (TF32 3x3: three items over two sets).  A set that skips a block must not arrive: skipping
+    // is not gated by the box's arrival, so it could arrive for a later round of the slot inside the current phase.
+    for (int i = 0; i < kWgRawSlots; ++i) { mbar_init(&rawp_full[i], 1); mbar_init(&rawp_empty[i], (!F16 && kTaps == 9) ? 8 : 4); }
     for (int i = 0; i < kWgQSlots; ++i) { mbar_init(&qraw_full[i], 1); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < kWgSets; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < kWgMaxPStages; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
     mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
@@ -188,88 +190,130 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
           }
           umma_commit(&p_empty[sp]);
-          if (++sp == kWgSets) { sp = 0; pp ^= 1; }
+          if (++sp == kPStages) { sp = 0; pp ^= 1; }
         }
         umma_commit(&q_empty[rq.slot]);
         MFLOW_WST(6, i, true);
       }
       umma_commit(&acc_full);
     }
-  } else if (warp < 2 + 4 * kWgSets) {
-    // ===== P transform: TMEM lane = input channel; set s (warps 2-5 / 6-9 / 10-13) handles the work items s, s + 3, ... =====
+  } else if (warp < 10) {
+    // ===== P transform: TMEM lane = input channel; two sets of four warps (warps 2-5 / 6-9) =====
     const int quad = warp & 3, set = (warp - 2) >> 2;
     const int ch = quad * 32 + lane;                          // channel within the p tile = TMEM lane
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-    const uint32_t t_p = tmem_p + t_lane + set * 2 * kPPart;
     float sx = 1.f, inv_sx = 1.f, sg = 1.f, inv_sg = 1.f;   // fp16 path: power-of-two operand scales
     if (F16) { pow2_scale_from_amax(a.x_amax, sx, inv_sx); pow2_scale_from_amax(a.g_amax, sg, inv_sg); }
 
     WgRing rp(a.n_raw);
-    int pp = 0, turn = 0;   // phase of this set's stage; owner (set) of the running (block, tap) work item
     constexpr bool kPad = kTaps == 9;
     constexpr int kImgs = kW == 4 ? 2 : 1;                       // images per 32-pixel block
     constexpr int kRows = kWgBlockPx / kW / kImgs, kBoxW = kPad ? kW + 8 : kW;   // rows per image in the block
     constexpr int kImgVec = kRows * kBoxW / 4;                   // float4s per (image, channel) in the raw box
     constexpr int kRawVec = kImgs * kImgVec;
-    for (int i = 0; i < n_my; ++i, rp.next()) {
-      bool loaded = false;
-      float raw[kRawVec * 4];
+    auto load_raw = [&](float (&raw)[kRawVec * 4]) {
+      // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
+      mbar_wait(&rawp_full[rp.slot], rp.phase);
+      const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + ch * kImgVec;   // box [image][channel][row][w]
 #pragma unroll
-      for (int t = 0; t < taps_here; ++t, turn = (turn + 1 == kWgSets ? 0 : turn + 1)) {
-        if (turn != set) continue;
-        if (!loaded) {
-          // the channel's rows of the block (halo included) -> registers with aligned 16-byte loads
-          mbar_wait(&rawp_full[rp.slot], rp.phase);
-          MFLOW_WST(4, i, set == 0 && quad == 0 && lane == 0);
-          const float4* src = reinterpret_cast<const float4*>(s_p + rp.slot * a.raw_bytes) + ch * kImgVec;   // box [image][channel][row][w]
+      for (int j = 0; j < kRawVec; ++j) {
+        const float4 v = src[(j / kImgVec) * 128 * kImgVec + (j % kImgVec)];
+        raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
+      }
+    };
+    if (F16) {
+      // set s owns the blocks of parity s; the (block, tap) items of ALL blocks walk the stage ring in order
+      int stage = 0, sphase = 0;
+      auto advance = [&](int n) { stage += n; if (stage >= kPStages) { stage -= kPStages; sphase ^= 1; } };
+      constexpr int kRowsTot = kRows * kImgs, kCvW = kPad ? kW + 2 : kW;   // converted pixels per row: the row and its halo
+      for (int i = 0; i < n_my; ++i, rp.next()) {
+        if ((i & 1) != set) { advance(taps_here); continue; }
+        float raw[kRawVec * 4];
+        load_raw(raw);
+        MFLOW_WST(4, i, set == 0 && quad == 0 && lane == 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);   // the box lives in registers now
+        uint32_t cv[kRowsTot * kCvW];                        // per pixel: {fp16 hi (low half), fp16 lo (high half)}
 #pragma unroll
-          for (int j = 0; j < kRawVec; ++j) {
-            const float4 v = src[(j / kImgVec) * 128 * kImgVec + (j % kImgVec)];
-            raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
+        for (int r = 0; r < kRowsTot; ++r)
+#pragma unroll
+          for (int j = 0; j < kCvW; ++j) {
+            float v = raw[r * kBoxW + (kPad ? 3 : 0) + j];
+            if (a.relu_in) v = fmaxf(v, 0.f);
+            v *= sx;
+            const float hf = __half2float(__float2half_rn(v));
+            const __half2 pk = __floats2half2_rn(v, v - hf);   // low half = fp16(v) again, high half = fp16(v - hi)
+            cv[r * kCvW + j] = *reinterpret_cast<const uint32_t*>(&pk);
           }
-          loaded = true;
-        }
-        mbar_wait(&p_empty[set], pp ^ 1);
-        pp ^= 1;
-        tc_fence_after();
-        // the 32 pixels shifted by this tap (x offset t - 1; box column = w + 4), ReLU, hi / lo split -> TMEM
-        auto pixel = [&](int px) -> float {
-          float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];   // rows of both images are consecutive in raw[]
-          return a.relu_in ? fmaxf(v, 0.f) : v;
-        };
-        if (F16) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {   // 16 pixels = 8 columns of packed fp16 pairs per part
+        for (int t = 0; t < taps_here; ++t) {
+          mbar_wait(&p_empty[stage], sphase ^ 1);
+          tc_fence_after();
+          const uint32_t t_p = tmem_p + t_lane + stage * 2 * kPPart;
+          // the 32 pixels shifted by this tap (x offset t - 1): pixel pair (px, px + 1) -> one column of packed hi halves
+          // and one of packed lo halves, each a byte permute of the two converted registers
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
             uint32_t h8[8], l8[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) split_f16x2(pixel(16 * j + 2 * c) * sx, pixel(16 * j + 2 * c + 1) * sx, h8[c], l8[c]);
+            for (int c = 0; c < 8; ++c) {
+              const int px = 16 * j + 2 * c, idx = (px / kW) * kCvW + (px % kW) + (kPad ? t : 0);
+              h8[c] = __byte_perm(cv[idx], cv[idx + 1], 0x5410);
+              l8[c] = __byte_perm(cv[idx], cv[idx + 1], 0x7632);
+            }
             tmem_st_32x8u(t_p + 8 * j, h8);
             tmem_st_32x8u(t_p + kPPart + 8 * j, l8);
           }
-        } else {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[stage]);
+          MFLOW_WST(7, i, t == 0 && quad == 0 && lane == 0);
+          advance(1);
+        }
+      }
+    } else {
+      // TF32: set s takes the (block, tap) work items of parity s and owns stage s
+      const uint32_t t_p = tmem_p + t_lane + set * 2 * kPPart;
+      int pp = 0, item = 0;   // phase of this set's stage; running work item
+      for (int i = 0; i < n_my; ++i, rp.next()) {
+        bool loaded = false;
+        float raw[kRawVec * 4];
+#pragma unroll
+        for (int t = 0; t < taps_here; ++t, ++item) {
+          if ((item & 1) != set) continue;
+          if (!loaded) {
+            load_raw(raw);
+            loaded = true;
+          }
+          mbar_wait(&p_empty[set], pp ^ 1);
+          pp ^= 1;
+          tc_fence_after();
+          // the 32 pixels shifted by this tap (x offset t - 1; box column = w + 4), ReLU, hi / lo split -> TMEM
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float h8[8], l8[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float v = pixel(8 * j + c);
+              const int px = 8 * j + c;
+              float v = raw[(px / kW) * kBoxW + (px % kW) + (kPad ? t + 3 : 0)];   // rows of both images are consecutive in raw[]
+              if (a.relu_in) v = fmaxf(v, 0.f);
               h8[c] = wg_trunc(v);
               l8[c] = wg_round(v - h8[c]);
             }
             tmem_st_32x8(t_p + 8 * j, h8);
             tmem_st_32x8(t_p + kPPart + 8 * j, l8);
           }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[set]);
         }
-        tmem_st_wait();
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[set]);
-        MFLOW_WST(7, i, t == 0 && quad == 0 && lane == 0);
+        if (lane == 0 && loaded) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box
       }
-      __syncwarp();
-      if (lane == 0 && loaded) mbar_arrive(&rawp_empty[rp.slot]);   // this warp is done with the block's raw box
     }
-    // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take every third 32-column chunk =====
+    // ===== epilogue: accumulators -> partial[ks][tap][ci][co]; the sets take alternate 32-column chunks =====
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const int ci = p0 + ch;
@@ -279,7 +323,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int t = 0; t < taps_here; ++t) {
       const int tap = kTaps == 9 ? dy * 3 + t : 0;
       float* dst = a.partial + (((int64_t)ks * a.taps + tap) * a.Cin + ci) * a.Cout + q0;
-      for (int c = set; c < n_chunks; c += kWgSets) {
+      for (int c = set; c < n_chunks; c += 2) {
         float v[32];
         tmem_ld_32x32(tmem + t_lane + t * a.n_tile + c * 32, v);
         if (ci < a.Cin) {
@@ -289,11 +333,11 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
       }
     }
-  } else if (warp >= 2 + 4 * kWgMaxSets) {
+  } else {
     // ===== Q split: the TMA-loaded fp32 tile becomes its TF32 hi part in place, the lo part goes next to it =====
     // These threads see every element of g_y exactly once, so the kernel-row-1 CTA of input-channel tile 0 also
     // accumulates the bias gradient sum_pixels g_y[co] (a thread's float4 positions are the same in every block).
-    const int tid = threadIdx.x - 32 * (2 + 4 * kWgMaxSets);   // 0..127
+    const int tid = threadIdx.x - 320;   // 0..127
     WgRing rq(kWgQSlots);
     const int n_vec = a.n_tile * (kWgBlockPx / 4);   // float4s of the tile
     const bool do_bias = a.bias_partial != nullptr && dy == (kTaps == 9 ? 1 : 0) && p0 == 0;
@@ -468,7 +512,7 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
   { const int widest = a.Cout < 128 ? a.Cout : 128; a.n_tile = (widest + 15) / 16 * 16; }
   a.tmem_cols = 512;
   a.x_amax = x_amax; a.g_amax = g_amax;
-  MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + (F16 ? 3 * kWgPCols : 4 * kWgPCols) <= 512, "accumulators do not fit in tensor memory");
+  MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + (F16 ? 5 * kWgPCols : 4 * kWgPCols) <= 512, "accumulators do not fit in tensor memory");
   const int n_ks = wgrad_splits(d);
   a.bias_partial = g_bias ? a.partial + (int64_t)n_ks * a.taps * a.Cin * a.Cout : nullptr;
 
