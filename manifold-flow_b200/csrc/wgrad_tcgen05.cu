@@ -231,8 +231,6 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         float raw[kRawVec * 4];
         load_raw(raw);
         MFLOW_WST(4, i, set == 0 && quad == 0 && lane == 0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);   // the box lives in registers now
         uint32_t cv[kRowsTot * kCvW];                        // per pixel: {fp16 hi (low half), fp16 lo (high half)}
 #pragma unroll
         for (int r = 0; r < kRowsTot; ++r)
@@ -245,6 +243,11 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const __half2 pk = __floats2half2_rn(v, v - hf);   // low half = fp16(v) again, high half = fp16(v - hi)
             cv[r * kCvW + j] = *reinterpret_cast<const uint32_t*>(&pk);
           }
+        // The box can go back to the producer once its values have been CONSUMED (not merely requested: an arrive right
+        // after the loads let the next TMA overwrite the slot under loads still in flight - wrong gradients at batch 256).
+        // Rows beyond the converted window are only halo padding, so every loaded register that matters is used above.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rawp_empty[rp.slot]);
 #pragma unroll
         for (int t = 0; t < taps_here; ++t) {
           mbar_wait(&p_empty[stage], sphase ^ 1);
