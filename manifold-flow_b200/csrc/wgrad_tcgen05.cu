@@ -46,7 +46,7 @@ constexpr int kWgMaxPStages = 5;                // P stages in tensor memory: 5 
 constexpr int kWgBlockPx = 32;                 // pixels per K block
 constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
 constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
-constexpr int kWgRawSlots = 3, kWgQSlots = 3;   // kWgRawSlots: at most (a.n_raw slots are used: 2 when the boxes are large)
+constexpr int kWgRawSlots = 3, kWgQSlots = 6;   // at most: a.n_raw (2 when the boxes are large) and a.n_q (what shared memory allows) are used
 
 struct WgradArgs {
   float* partial;   // [ks][taps][Cin][Cout]
@@ -58,6 +58,7 @@ struct WgradArgs {
   int box_w;        // raw activation box width: W + 8 (3x3, starts 4 pixels left: TMA needs 16-byte aligned starts) or W
   int raw_bytes;    // one raw activation box [images][128 ci][rows][box_w] fp32
   int n_raw;        // raw-box ring depth (2 or 3)
+  int n_q;          // Q-tile ring depth (3 .. kWgQSlots): the chain TMA -> split -> MMA -> slot free is ~3000 cycles long
   int n_tile;       // MMA N extent (output channels of this launch's q tile, multiple of 16, <= 128)
   int blocks_per_img;  // H * W / 32
   int n_blocks;     // B * blocks_per_img
@@ -95,7 +96,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;                                   // kWgQSlots x {Q_hi 16 KB, Q_lo 16 KB}
-  uint8_t* s_p = s_q + kWgQSlots * 2 * kWgQBytes;        // kWgRawSlots x raw activation box
+  uint8_t* s_p = s_q + a.n_q * 2 * kWgQBytes;            // a.n_raw x raw activation box
   __shared__ __align__(8) uint64_t rawp_full[kWgRawSlots], rawp_empty[kWgRawSlots], qraw_full[kWgQSlots], q_full[kWgQSlots],
       q_empty[kWgQSlots], p_full[kWgMaxPStages], p_empty[kWgMaxPStages], acc_full;
   __shared__ uint32_t s_tmem;
@@ -135,7 +136,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      WgRing rp(a.n_raw), rq(kWgQSlots);
+      WgRing rp(a.n_raw), rq(a.n_q);
       for (int i = 0; i < n_my; ++i, rp.next(), rq.next()) {
         const int blk = blk0 + i;
         // image and 32-pixel block within it; 4x4 maps: one block = two whole images
@@ -155,7 +156,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     // ===== MMA issuer =====
     if (elect_one()) {
       const uint32_t idesc = F16 ? idesc_f16(128, a.n_tile, 0, 0) : idesc_tf32(128, a.n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
-      WgRing rq(kWgQSlots);
+      WgRing rq(a.n_q);
       int sp = 0, pp = 0;   // P stage and its phase; one stage per (block, tap) work item
       for (int i = 0; i < n_my; ++i, rq.next()) {
         mbar_wait(&q_full[rq.slot], rq.phase);
@@ -341,7 +342,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     // These threads see every element of g_y exactly once, so the kernel-row-1 CTA of input-channel tile 0 also
     // accumulates the bias gradient sum_pixels g_y[co] (a thread's float4 positions are the same in every block).
     const int tid = threadIdx.x - 320;   // 0..127
-    WgRing rq(kWgQSlots);
+    WgRing rq(a.n_q);
     const int n_vec = a.n_tile * (kWgBlockPx / 4);   // float4s of the tile
     const bool do_bias = a.bias_partial != nullptr && dy == (kTaps == 9 ? 1 : 0) && p0 == 0;
     float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // n_vec <= 1024 = 8 x 128
@@ -355,11 +356,19 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       float4* lo = reinterpret_cast<float4*>(s_q + rq.slot * 2 * kWgQBytes + kWgQBytes);
       uint8_t* f16_hi = s_q + rq.slot * 2 * kWgQBytes + kWgQHiOff;
       uint8_t* f16_lo = s_q + rq.slot * 2 * kWgQBytes + kWgQLoOff;
+      // all loads first: the stores below go to the same shared memory, so the compiler keeps every later load behind
+      // every earlier store - interleaved, the seven 16-byte chunks of a thread formed one serial latency chain
+      float4 vq[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = tid + 128 * k;
+        vq[k] = j < n_vec ? hi[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int j = tid + 128 * k;
         if (j < n_vec) {
-          const float4 v = hi[j];
+          const float4 v = vq[k];
           bsum[k] += (v.x + v.y) + (v.z + v.w);
           if (F16) {
             // float4 j of the TMA-swizzled fp32 tile -> (row r, 4-pixel group c8 of the 32-pixel block) -> 8 bytes of the
@@ -533,7 +542,9 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
     if (!encode(&mg, g_y, 3, dims, str, box, imgs == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return MFLOW_E_BADARG;
   }
   dim3 grid(n_ks, a.n_dy, q_tiles * p_tiles);
-  const size_t smem = (size_t)kWgQSlots * 2 * kWgQBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
+  a.n_q = (226 * 1024 - 1024 - a.n_raw * a.raw_bytes) / (2 * kWgQBytes);
+  a.n_q = a.n_q > kWgQSlots ? kWgQSlots : (a.n_q < 3 ? 3 : a.n_q);
+  const size_t smem = (size_t)a.n_q * 2 * kWgQBytes + (size_t)a.n_raw * a.raw_bytes + 1024;
   const cudaStream_t st = (cudaStream_t)stream;
   int dev = 0;
   cudaGetDevice(&dev);
