@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a captured CUDA graph")
     ap.add_argument("--reduce", default="trained", choices=["trained", "all"],
                     help="N > 1: all-reduce the gradients of the parameter group the phase trains (experiments/train.py:287-297) or of all parameters")
+    ap.add_argument("--allreduce", default="after-replay", choices=["after-replay", "in-graph"],
+                    help="N > 1 with a captured step: all-reduce the gradient buckets right after the replay, on the same stream (default), or from "
+                         "backward hooks inside the captured graph (experimental: NCCL kernels become graph nodes)")
     ap.add_argument("--detail", default=None, help="write the per-kernel breakdown (JSON) to this path")
     return ap.parse_args()
 
@@ -361,16 +364,19 @@ def run_b200(args):
                 model(dev_pool[0][0], mode="projection", context=dev_pool[0][1])
     ddp.broadcast_parameters(model, src=0)
     use_graph = not args.no_graph
-    # Multi-GPU: the gradient buckets of the TRAINED parameter group are all-reduced (NCCL, averaged in the reduction) from
-    # the hooks of backward, i.e. overlapped with the rest of backward and captured into the same CUDA graph.
+    # Multi-GPU: the flat gradient buckets of the TRAINED parameter group (experiments/train.py:287-297) are all-reduced
+    # with NCCL, averaged in the reduction.  Eager steps and --allreduce in-graph: from the hooks of backward, overlapped
+    # with the rest of backward.  Captured step (default): the graph holds this rank's forward + backward, the bucket
+    # all-reduces follow the replay on the same stream.
     reducer = None
     reduced_bytes = 0
+    in_graph = args.allreduce == "in-graph"
     if world > 1 and train:
         group = model.parameters() if (args.reduce == "all" or C["trained"] == "all") else getattr(model, C["trained"]).parameters()
-        reducer = ddp.GradientAllReducer(group, bucket_mb=64.0, overlap=True)
+        reducer = ddp.GradientAllReducer(group, bucket_mb=64.0, overlap=(not use_graph) or in_graph)
         reduced_bytes = reducer.payload_bytes()
 
-    def step(x, c):
+    def step(x, c, reduce=True):
         """one whole step on this rank's shard: forward + backward (+ bucket all-reduces)"""
         if not train:
             with torch.no_grad():
@@ -386,7 +392,7 @@ def run_b200(args):
         lp = forward(x, c)
         loss = -lp.mean()
         loss.backward()
-        if reducer is not None:
+        if reducer is not None and reduce:
             reducer.finish()
         return loss, lp.detach()
 
@@ -408,8 +414,10 @@ def run_b200(args):
                 model.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                static_loss, static_lp = step(static_x, static_c)
+                static_loss, static_lp = step(static_x, static_c, reduce=in_graph)
             graph.replay()
+            if reducer is not None and not in_graph:
+                reducer.finish()
             torch.cuda.synchronize()
         except Exception as exc:  # capture is an optimisation: report and fall back to eager launches
             print(f"[bench] CUDA graph capture failed, running eagerly: {type(exc).__name__}: {str(exc)[:300]}", file=sys.stderr)
@@ -430,6 +438,8 @@ def run_b200(args):
         if static_c is not None:
             static_c.copy_(c, non_blocking=True)
         graph.replay()
+        if reducer is not None and not in_graph:
+            reducer.finish()
         return static_loss, static_lp
 
     def barrier():
@@ -599,7 +609,9 @@ def run_b200(args):
             "dtype": "f32" if config.conditioner_math == "fp32" else "f32 (tf32 conditioner GEMMs)", "data": "synthetic",
             "config": {"workload": C["workload"], "name": cfg, "global_batch": world * b, "per_gpu_batch": b, "parallelism": f"dp{world}",
                        "l2": working_set_note,
-                       "allreduce": (f"{reduced_bytes} B per step: gradients of the trained group ({C['trained']}), NCCL AVG, issued from backward hooks inside the captured graph"
+                       "allreduce": (f"{reduced_bytes} B per step: gradients of the trained group ({C['trained'] if args.reduce == 'trained' else 'all'}), NCCL AVG, "
+                                     + ("issued from backward hooks inside the captured graph" if (in_graph and graph is not None) else
+                                        "after the graph replay on the same stream" if graph is not None else "from backward hooks (eager)")
                                      if reducer is not None else None)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_secs / args.steps},

@@ -1,6 +1,6 @@
 """GPU, 2 ranks over NCCL (needs two devices: `gpurun --gpus 2`): the data-parallel step of the reduced gan64d-shaped
 M-flow gives the gradients of one rank on the whole batch (<= 1e-6 relative up to reduction
-order), eagerly and as a captured CUDA graph with the NCCL all-reduces inside."""
+order), eagerly (all-reduces overlapped with backward) and as a replayed CUDA graph followed by the bucket all-reduces."""
 import os
 import socket
 
@@ -46,27 +46,30 @@ def _worker(rank, world, port, out):
     xs, cs = x[lo:hi].to(dev), ctx[lo:hi].to(dev)
     reducer = ddp.GradientAllReducer(model.parameters(), bucket_mb=1.0, overlap=True)
 
-    def step(a, c):
+    def step(a, c, reduce=True):
         reducer.zero_grad()
         lp = model(a, mode="mf-fixed-manifold", context=c)[1]
         (-lp.sum() / n).backward()          # global mean: every rank contributes its shard's share ...
-        reducer.finish()                    # ... averaged over ranks -> multiply by world below
+        if reduce:
+            reducer.finish()                # ... averaged over ranks -> multiply by world below
 
-    step(xs, cs)
-    eager = {k: g * world for k, g in _grads(model).items()}
-    # the same step captured as one CUDA graph, NCCL kernels included
+    # every backward runs on the side stream (one on the default stream before a capture would tie the parameters'
+    # gradient accumulators to the legacy stream, which a capturing stream may not wait for)
     sx, sc = xs.clone(), cs.clone()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for _ in range(11):
-            step(sx, sc)
+        for _ in range(3):
+            step(sx, sc)                    # eager: bucket all-reduces issued from the backward hooks
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    eager = {k: g * world for k, g in _grads(model).items()}
+    # what bench.py does: this rank's forward + backward replayed as one CUDA graph, bucket all-reduces after the replay
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-        step(sx, sc)
+    with torch.cuda.graph(graph):
+        step(sx, sc, reduce=False)
     graph.replay()
+    reducer.finish()
     torch.cuda.synchronize()
     replay = {k: g * world for k, g in _grads(model).items()}
     if rank == 0:
