@@ -324,6 +324,11 @@ def load_json(path):
 # ---------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------
+def _trace(msg):
+    if os.environ.get("MFLOW_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(args):
     from manifold_flow.b200 import cabi, config, ddp, factory
     import golden_util as gu
@@ -362,7 +367,9 @@ def run_b200(args):
                 model.log_prob(dev_pool[0][0], context=dev_pool[0][1])
             else:
                 model(dev_pool[0][0], mode="projection", context=dev_pool[0][1])
+    _trace("actnorm init done")
     ddp.broadcast_parameters(model, src=0)
+    _trace("parameters broadcast")
     use_graph = not args.no_graph
     # Multi-GPU: the flat gradient buckets of the TRAINED parameter group (experiments/train.py:287-297) are all-reduced
     # with NCCL, averaged in the reduction.  Eager steps and --allreduce in-graph: from the hooks of backward, overlapped
@@ -406,19 +413,23 @@ def run_b200(args):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(3 if world == 1 else 11):
+                for it in range(3 if world == 1 else 11):
                     step(static_x, static_c)
+                    _trace(f"warm-up step {it} issued")
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            _trace("warm-up done")
             if reducer is None:
                 model.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss, static_lp = step(static_x, static_c, reduce=in_graph)
+            _trace("captured")
             graph.replay()
             if reducer is not None and not in_graph:
                 reducer.finish()
             torch.cuda.synchronize()
+            _trace("first replay done")
         except Exception as exc:  # capture is an optimisation: report and fall back to eager launches
             print(f"[bench] CUDA graph capture failed, running eagerly: {type(exc).__name__}: {str(exc)[:300]}", file=sys.stderr)
             graph = None
@@ -471,8 +482,10 @@ def run_b200(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms) / 1e3, h2d, d2h
 
+    _trace("graph phase over")
     n_before = cabi.launch_count
     step(*dev_pool[1 % len(dev_pool)])
+    _trace("eager step done")
     launches_per_step_eager = cabi.launch_count - n_before  # libmflow_b200 kernels in one step (a graph replays the same)
     for i in range(max(args.warmup, 3)):
         run_step(*dev_pool[i % len(dev_pool)])
@@ -493,13 +506,15 @@ def run_b200(args):
 
     # ---- parity of the path that was just timed: log_prob of a replayed batch against the oracle on the CPU ----
     parity = None
+    if not args.no_parity:
+        _, lp_chk = run_step(dev_pool[2][0], dev_pool[2][1])   # every rank: the step may contain collectives
+        torch.cuda.synchronize()
     if rank == 0 and not args.no_parity:
         import mflow_oracle as oracle
 
         n_chk = min(b, 8 if C["dim"] is None else (64 if kind == "eval_mf" else 256))
         xh, ch = pool[2]
-        _, lp = run_step(dev_pool[2][0], dev_pool[2][1])
-        got = lp[:n_chk].float().cpu()
+        got = lp_chk[:n_chk].float().cpu()
         sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         sd64 = {k: (v.double() if torch.is_floating_point(v) else v) for k, v in sd_cpu.items()}
         om = oracle.config_model(cfg)

@@ -65,6 +65,13 @@ def _worker(rank, world, port, out):
     torch.cuda.synchronize()
     eager = {k: g * world for k, g in _grads(model).items()}
     # what bench.py does: this rank's forward + backward replayed as one CUDA graph, bucket all-reduces after the replay
+    # (no hooks: an all-reduce issued from a hook during capture would become a graph node)
+    reducer.close()
+    reducer = ddp.GradientAllReducer(model.parameters(), bucket_mb=1.0, overlap=False)
+    with torch.cuda.stream(side):
+        step(sx, sc)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         step(sx, sc, reduce=False)
