@@ -180,6 +180,30 @@ MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const flo
                            int64_t rows, int64_t n, int32_t inverse, float cut_point, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (b') Vector conditioner: the whole ResidualNet (manifold_flow/nn/resnet.py:9-72) in one launch.
+ *   h = W_0 [x | ctx] + b_0;  per block: h += gate * (W_b relu(W_a relu(h) + b_a) + b_b),
+ *   gate = sigmoid(W_c ctx + b_c) when n_ctx > 0 (the GLU of :38-39), else 1;  out = W_f h + b_f.
+ *   x: input feature c of row r at x[r * x_ld + c * x_step] (the coupling layer's identity features, read in
+ *   place); ctx [rows, n_ctx] with row pitch ctx_ld or NULL; out [rows, n_out] contiguous.
+ *   weights / biases: HOST arrays of device pointers in the order first, (lin_a, lin_b[, gate]) per block, last -
+ *   nn.Linear layout weight [out_features, in_features].  hidden <= 128, n_in + n_ctx <= 128, n_blocks <= 4.
+ * Backward: recomputes the forward per row tile (only x and ctx are kept), writes g_x [rows, n_in] (may be NULL)
+ * and every weight / bias gradient (same order as weights / biases; deterministic row-ordered reduction);
+ * workspace: mflow_mlp_workspace_floats(desc) floats.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t rows;
+  int32_t n_in, n_ctx, hidden, n_out, n_blocks;
+} mflow_mlp_desc;
+MFLOW_API int64_t mflow_mlp_workspace_floats(const mflow_mlp_desc* desc);
+MFLOW_API int mflow_mlp_forward(const mflow_mlp_desc* desc, const float* x, int64_t x_ld, int64_t x_step, const float* ctx,
+                      int64_t ctx_ld, const float* const* weights, const float* const* biases, float* out,
+                      void* stream);
+MFLOW_API int mflow_mlp_backward(const mflow_mlp_desc* desc, const float* x, int64_t x_ld, int64_t x_step, const float* ctx,
+                       int64_t ctx_ld, const float* const* weights, const float* const* biases, const float* g_out,
+                       float* g_x, float* const* g_weights, float* const* g_biases, float* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (b) Conditioner convolutions on tcgen05 tensor cores (error-compensated 3-product split: fp32-accurate).
  * Replaces nn.Conv2d 3x3 (pad 1) / 1x1 + bias (+ pre-activation ReLU, + residual, + ReLU) of
  * ConvResidualNet / ConvResidualBlock (manifold_flow/nn/resnet.py:75-142).

@@ -46,6 +46,12 @@ class RqsBoxDesc(ctypes.Structure):
     ]
 
 
+class MlpDesc(ctypes.Structure):
+    """mflow_mlp_desc"""
+
+    _fields_ = [("rows", i64), ("n_in", i32), ("n_ctx", i32), ("hidden", i32), ("n_out", i32), ("n_blocks", i32)]
+
+
 class ConvDesc(ctypes.Structure):
     """mflow_conv_desc"""
 
@@ -76,6 +82,10 @@ _SIGNATURES = {
     "mflow_rqs_box_apply": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 6),
     "mflow_rqs_box_backward": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 8),
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),
+    "mflow_mlp_workspace_floats": (i64, [ctypes.POINTER(MlpDesc)]),
+    "mflow_mlp_forward": (ctypes.c_int, [ctypes.POINTER(MlpDesc), c_f32p, i64, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "mflow_mlp_backward": (ctypes.c_int, [ctypes.POINTER(MlpDesc), c_f32p, i64, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                          c_f32p, c_f32p, c_f32p]),
     "mflow_conv2d_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
     "mflow_conv2d_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 11),
     "mflow_conv2d_wgrad_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),

@@ -93,6 +93,16 @@ def residual_net_planes(net, inputs, context):
     return out.view(out.shape[0], out.shape[1], w * w).transpose(1, 2).reshape(rows, out.shape[1])
 
 
+def residual_net_fused(net, inputs, context):
+    """ResidualNet (nn/resnet.py:43-72) as one fused launch (``mflow_mlp_forward``: all layers, ReLUs, GLU context gates and
+    skip connections; the identity features are read in place from the coupling layer's input), or None when the shape
+    does not qualify (hidden > 128 features, context that needs a gradient, ...)."""
+    if not (config.fuse_vector_conditioner and config.conditioner_math == "fp32" and ops.mlp_fused_supported(net, inputs, context)):
+        return None
+    require_cuda(inputs)
+    return ops.residual_net_fused(net, inputs, context)
+
+
 def residual_block_conv(x, conv0, conv1, gate_layer, context):
     """nn/resnet.py:91-104"""
     require_cuda(x)

@@ -20,6 +20,9 @@ class _Config:
     # kernels (a Linear layer is a 1x1 convolution once the batch rows are laid out as pixels); below it the
     # 2-CTA launches are latency bound and the cuBLAS sgemm calls are faster
     linear_tc_min_rows = int(os.environ.get("MFLOW_LINEAR_TC_MIN_ROWS", "32768"))
+    # below that row count: the whole ResidualNet as one fused launch (mflow_mlp_forward / _backward); False = one cuBLAS
+    # GEMM and a few ATen launches per layer
+    fuse_vector_conditioner = os.environ.get("MFLOW_FUSE_MLP", "1") != "0"
     # build the dense L / U / W / W^-1 matrices of all same-width LU layers of a model in one batched pass
     batch_lu_builds = os.environ.get("MFLOW_BATCH_LU", "1") != "0"
     # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch

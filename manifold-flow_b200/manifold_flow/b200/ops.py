@@ -12,7 +12,7 @@ import torch
 
 from . import cabi
 from .config import config
-from .cabi import ConvDesc, MixDesc, RqsBoxDesc, RqsDesc, check, lib, ptr, require_cuda, stream
+from .cabi import ConvDesc, MixDesc, MlpDesc, RqsBoxDesc, RqsDesc, check, lib, ptr, require_cuda, stream
 
 
 def _c(t):
@@ -435,6 +435,70 @@ class _ConvTC(torch.autograd.Function):
         if want_bias and gb is None:
             gb = channel_sum(g)
         return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None, None
+
+
+# --------------------------------------------------------------------------------------------
+# (b') vector conditioner: the whole ResidualNet in one launch (nn/resnet.py:9-72)
+# --------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def mlp_fused_supported(net, inputs, context):
+    n_ctx = 0 if context is None else context.shape[1]
+    return (inputs.dim() == 2 and net.hidden_features <= 128 and inputs.shape[1] + n_ctx <= 128 and len(net.blocks) <= 4
+            and net.final_layer.out_features <= 8192 and (context is None or (context.dim() == 2 and not context.requires_grad))
+            and inputs.stride(1) >= 1 and inputs.stride(0) >= 1)
+
+
+class _MlpFused(torch.autograd.Function):
+    """(x view, ctx, weights..., biases...) -> conditioner output [rows, n_out].  x may be a strided 2-D view (the identity
+    features of a coupling layer): it is read in place."""
+
+    @staticmethod
+    def forward(ctx, x, context, n_layers, n_blocks, *params):
+        weights, biases = params[:n_layers], params[n_layers:]
+        require_cuda(x, context, *params)
+        context = None if context is None else _c(context)
+        weights, biases = [_c(w) for w in weights], [_c(b) for b in biases]
+        rows, n_in = x.shape
+        n_ctx = 0 if context is None else context.shape[1]
+        d = MlpDesc(rows=rows, n_in=n_in, n_ctx=n_ctx, hidden=weights[0].shape[0], n_out=weights[-1].shape[0], n_blocks=n_blocks)
+        out = torch.empty((rows, d.n_out), dtype=torch.float32, device=x.device)
+        check(lib().mflow_mlp_forward(ctypes.byref(d), ptr(x), x.stride(0), x.stride(1), ptr(context), n_ctx, _ptr_array(weights),
+                                      _ptr_array(biases), ptr(out), stream()), "mflow_mlp_forward")
+        cabi.count_launch()
+        ctx.desc, ctx.n_layers = d, n_layers
+        ctx.save_for_backward(x, context, *weights, *biases)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, context, *params = ctx.saved_tensors
+        n_layers, d = ctx.n_layers, ctx.desc
+        weights, biases = params[:n_layers], params[n_layers:]
+        g_out = _c(g_out)
+        g_x = torch.empty((d.rows, d.n_in), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        g_w = [torch.empty_like(w) for w in weights]
+        g_b = [torch.empty_like(b) for b in biases]
+        ws = cabi.workspace("mlp", 4 * lib().mflow_mlp_workspace_floats(ctypes.byref(d)), x.device)
+        check(lib().mflow_mlp_backward(ctypes.byref(d), ptr(x), x.stride(0), x.stride(1), ptr(context), d.n_ctx, _ptr_array(weights),
+                                       _ptr_array(biases), ptr(g_out), ptr(g_x), _ptr_array(g_w), _ptr_array(g_b), ptr(ws), stream()),
+              "mflow_mlp_backward")
+        cabi.count_launch(2)
+        return (g_x, None, None, None) + tuple(g_w) + tuple(g_b)
+
+
+def residual_net_fused(net, inputs, context):
+    """ResidualNet forward through ``mflow_mlp_forward`` (one launch; two for the backward)."""
+    layers = [net.initial_layer]
+    for block in net.blocks:
+        layers += [block.linear_layers[0], block.linear_layers[1]]
+        if context is not None:
+            layers.append(block.context_layer)
+    layers.append(net.final_layer)
+    params = [layer.weight for layer in layers] + [layer.bias for layer in layers]
+    return _MlpFused.apply(inputs, context, len(layers), len(net.blocks), *params)
 
 
 # --------------------------------------------------------------------------------------------

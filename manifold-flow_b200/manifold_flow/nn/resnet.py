@@ -59,6 +59,9 @@ class ResidualNet(nn.Module):
         out = K.residual_net_planes(self, inputs, context)   # large batches: tensor-core path
         if out is not None:
             return out
+        out = K.residual_net_fused(self, inputs, context)    # everything else: the whole net in one launch
+        if out is not None:
+            return out
         temps = K.linear(inputs if context is None else torch.cat((inputs, context), dim=1), self.initial_layer)
         for block in self.blocks:
             temps = block(temps, context=context)

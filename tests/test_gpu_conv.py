@@ -213,3 +213,59 @@ def test_conv_at_bench_batch_vs_fp64(cuda_device, case):
         tol = 1e-4 if name in ("grad_w", "grad_b") else 2e-5
         assert _rel(a, r) <= tol, f"{name}: rel L2 error {_rel(a, r):.2e}"
         assert float((a.double() - r).abs().max()) <= 10 * tol * float(r.abs().max()), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,d_full,n_out,ctx,even", [(100, 40, 640, None, True), (256, 14, 224, 2, False), (256, 64, 1024, 1, True),
+                                                         (1000, 3, 23, None, False), (5, 2, 29, 1, True), (2051, 40, 640, None, False)])
+def test_fused_vector_conditioner_matches_fp64(cuda_device, rows, d_full, n_out, ctx, even):
+    """mflow_mlp_forward / _backward (the whole ResidualNet of a coupling layer as one launch, reference
+    nn/resnet.py:9-72) against an fp64 evaluation of the same formulas: outputs and every gradient, with the identity
+    features read in place from a strided view of the coupling layer's input.  Rows with a pre-activation within 1e-4 of
+    the ReLU kink get a zero incoming gradient (there the fp32 and fp64 masks may legitimately differ)."""
+    from manifold_flow import nn as nn_
+    from manifold_flow.b200 import cabi, ops
+
+    torch.manual_seed(rows + n_out)
+    full = torch.randn(rows, d_full, device=cuda_device, requires_grad=True)
+    x = full[:, (1 if even else 0)::2]            # the identity features of an alternating mask: a strided view
+    n_in = x.shape[1]
+    net = nn_.ResidualNet(n_in, n_out, hidden_features=100, context_features=ctx, num_blocks=2).to(cuda_device)
+    for p in net.parameters():
+        p.data.normal_(0.0, 0.2)
+    c = None if ctx is None else torch.randn(rows, ctx, device=cuda_device)
+    g = torch.randn(rows, n_out, device=cuda_device)
+
+    P = {n: p.detach().double().requires_grad_() for n, p in net.named_parameters()}
+    x64 = x.detach().double().requires_grad_()
+    c64 = None if c is None else c.double()
+    h = F.linear(x64 if c is None else torch.cat((x64, c64), 1), P["initial_layer.weight"], P["initial_layer.bias"])
+    near_kink = torch.zeros(rows, dtype=torch.bool, device=cuda_device)
+    for i in range(2):
+        near_kink |= h.detach().abs().min(dim=1).values < 1e-4
+        t = F.linear(F.relu(h), P[f"blocks.{i}.linear_layers.0.weight"], P[f"blocks.{i}.linear_layers.0.bias"])
+        near_kink |= t.detach().abs().min(dim=1).values < 1e-4
+        t = F.linear(F.relu(t), P[f"blocks.{i}.linear_layers.1.weight"], P[f"blocks.{i}.linear_layers.1.bias"])
+        if c is not None:
+            t = t * torch.sigmoid(F.linear(c64, P[f"blocks.{i}.context_layer.weight"], P[f"blocks.{i}.context_layer.bias"]))
+        h = h + t
+    y64 = F.linear(h, P["final_layer.weight"], P["final_layer.bias"])
+    g = g * (~near_kink)[:, None]
+    y64.backward(g.double())
+
+    n0 = cabi.launch_count
+    y = net(x, c)
+    assert cabi.launch_count - n0 == 1, "the conditioner must be ONE launch of libmflow_b200"
+    y.backward(g)
+    assert cabi.launch_count - n0 == 3
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(y, y64.detach()) < 1e-5
+    assert rel(full.grad[:, (1 if even else 0)::2], x64.grad) < 2e-5
+    assert float(full.grad[:, (0 if even else 1)::2].abs().max()) == 0.0
+    for n, p in net.named_parameters():
+        assert rel(p.grad, P[n].grad) < 2e-5, n
+    # deterministic: the row-ordered parameter-gradient reduction gives the same bits on a second pass
+    first = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    net(x, c).backward(g)
+    assert all(torch.equal(first[n], p.grad) for n, p in net.named_parameters())
