@@ -8,9 +8,9 @@
 // `glu(cat(t, context_layer(ctx)))` = t * sigmoid(context_layer(ctx)), :38-39).  The reference issues six small GEMMs
 // and ~10 pointwise launches per evaluation (~55 with the backward bookkeeping), each moving a [B, 100] activation through
 // HBM; at the batch sizes the BASELINE configs run (100 .. a few thousand rows) that is pure launch latency.  Here a CTA
-// owns R rows, keeps every activation of those rows in shared memory and walks the layers; the weights (<= 100 x 100
-// per hidden layer) stream from L2 in 32-column chunks that are transposed through shared memory, so every global
-// read is a full 128-byte line and every shared read is conflict free.  fp32 FMA throughout: with M = R rows per CTA this
+// owns R rows, keeps every activation of those rows in shared memory and walks the layers; thread j owns output
+// feature j and streams its weight row (<= 100 floats per hidden layer, L1 / L2 resident) with 16-byte loads while the
+// activations arrive as broadcast 16-byte shared loads.  fp32 FMA throughout: with M = R rows per CTA this
 // is not tensor-core shaped (from 32768 rows on the conditioner runs on the tcgen05 convolution kernels instead,
 // manifold_flow/b200/conditioner.py).
 //
@@ -25,7 +25,6 @@ namespace mflow {
 
 constexpr int kMlpThreads = 128;   // one thread per hidden feature (hidden <= 128)
 constexpr int kMlpMaxBlocks = 4;
-constexpr int kMlpChunk = 32;      // weight columns staged per step
 
 struct MlpLayer {
   const float* w;   // [J][K] row-major (nn.Linear.weight)
@@ -46,44 +45,60 @@ struct MlpArgs {
 };
 
 // dense layer for the CTA's R rows: acc[r] = bias[j] + sum_k W[j][k] act[r][k] for this thread's output feature j.
-// act: shared [R][ld]; W chunks are staged transposed in s_w [kMlpChunk][kMlpThreads].
+// act: shared [R][ld] (ld % 4 == 0).  The thread walks ITS weight row with 16-byte loads (a row is a run of full 128-byte
+// lines, served by L1 after the first touch) and reads the activations as broadcast 16-byte shared loads: per four k
+// one LDG.128 + R LDS.128 feed 4R FMAs.  Rows whose length is not a multiple of 4 (the first layer: in + context
+// features; the context gates) take the scalar loop.  The caller synchronises around writes to act.
 template <int R>
-__device__ __forceinline__ void dense_rows(const MlpLayer& L, int j, const float* act, int ld, float* s_w, float (&acc)[R]) {
+__device__ __forceinline__ void dense_rows(const MlpLayer& L, int j, const float* act, int ld, float (&acc)[R]) {
   const float bias = (j < L.J) ? __ldg(L.b + j) : 0.f;
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = bias;
-  for (int k0 = 0; k0 < L.K; k0 += kMlpChunk) {
-    __syncthreads();   // previous chunk consumed (and act complete on the first pass)
-    // stage W[j][k0 .. k0+32) transposed: thread j reads one contiguous 128-byte piece of its row
-    if (j < L.J) {
-      const float* wr = L.w + (int64_t)j * L.K + k0;
+  if (j >= L.J) return;
+  const float* wr = L.w + (int64_t)j * L.K;
+  if ((L.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(act)) & 15) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll 4
+    for (int k4 = 0; k4 < L.K / 4; ++k4) {
+      const float4 w = __ldg(w4 + k4);
 #pragma unroll
-      for (int c = 0; c < kMlpChunk; ++c) s_w[c * kMlpThreads + j] = (k0 + c < L.K) ? __ldg(wr + c) : 0.f;
-    }
-    __syncthreads();
-    const int kn = min(kMlpChunk, L.K - k0);
-    if (j < L.J) {
-      for (int c = 0; c < kn; ++c) {
-        const float w = s_w[c * kMlpThreads + j];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = fmaf(w, act[r * ld + k0 + c], acc[r]);
+      for (int r = 0; r < R; ++r) {
+        const float4 a4 = *reinterpret_cast<const float4*>(act + r * ld + 4 * k4);
+        acc[r] = fmaf(w.x, a4.x, fmaf(w.y, a4.y, fmaf(w.z, a4.z, fmaf(w.w, a4.w, acc[r]))));
       }
+    }
+  } else {
+    for (int k = 0; k < L.K; ++k) {
+      const float w = __ldg(wr + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(w, act[r * ld + k], acc[r]);
     }
   }
 }
 
 // transposed product for the backward pass: acc[r] = sum_j W[j][k] g[r][j] for this thread's INPUT feature k
-// (threads read W[j][k] for consecutive k: coalesced in the original layout)
+// (threads read W[j][k] for consecutive k: coalesced in the original layout); g: shared [R][ld], ld % 4 == 0
 template <int R>
 __device__ __forceinline__ void dense_rows_t(const MlpLayer& L, int k, const float* g, int ld, float (&acc)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  if (k < L.K) {
-    for (int j = 0; j < L.J; ++j) {
-      const float w = __ldg(L.w + (int64_t)j * L.K + k);
+  if (k >= L.K) return;
+  const float* wc = L.w + k;
+  int j = 0;
+#pragma unroll 2
+  for (; j + 4 <= L.J; j += 4) {
+    const float w0 = __ldg(wc + (int64_t)j * L.K), w1 = __ldg(wc + (int64_t)(j + 1) * L.K), w2 = __ldg(wc + (int64_t)(j + 2) * L.K),
+                w3 = __ldg(wc + (int64_t)(j + 3) * L.K);
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmaf(w, g[r * ld + j], acc[r]);
+    for (int r = 0; r < R; ++r) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + r * ld + j);
+      acc[r] = fmaf(w0, g4.x, fmaf(w1, g4.y, fmaf(w2, g4.z, fmaf(w3, g4.w, acc[r]))));
     }
+  }
+  for (; j < L.J; ++j) {
+    const float w = __ldg(wc + (int64_t)j * L.K);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = fmaf(w, g[r * ld + j], acc[r]);
   }
 }
 
@@ -94,8 +109,7 @@ constexpr int kLd = kMlpThreads;   // row pitch of the shared activation arrays
 // the forward of the CTA's rows up to (not including) the final layer; optionally records the intermediates the
 // backward needs: s_keep holds, per block, {h_in, t (pre-ReLU output of lin_a), u (pre-gate output of lin_b), gate}
 template <int R, bool KEEP>
-__device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows, float* s_in, float* s_h, float* s_act, float* s_w,
-                                          float* s_keep) {
+__device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows, float* s_in, float* s_h, float* s_act, float* s_keep) {
   const int j = threadIdx.x;
   const int n0 = a.n_in + a.n_ctx;
   // inputs [x | ctx] -> shared
@@ -109,7 +123,8 @@ __device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows,
     s_in[idx] = v;
   }
   float acc[R];
-  dense_rows<R>(a.first, j, s_in, kLd, s_w, acc);
+  __syncthreads();
+  dense_rows<R>(a.first, j, s_in, kLd, acc);
 #pragma unroll
   for (int r = 0; r < R; ++r) s_h[r * kLd + j] = (j < a.hidden) ? acc[r] : 0.f;
   for (int blk = 0; blk < a.n_blocks; ++blk) {
@@ -121,7 +136,8 @@ __device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows,
       if (KEEP) keep[r * kLd + j] = h;
       s_act[r * kLd + j] = fmaxf(h, 0.f);
     }
-    dense_rows<R>(a.lin_a[blk], j, s_act, kLd, s_w, acc);
+    __syncthreads();
+    dense_rows<R>(a.lin_a[blk], j, s_act, kLd, acc);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -129,13 +145,14 @@ __device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows,
       s_act[r * kLd + j] = fmaxf(acc[r], 0.f);
     }
     float u[R];
-    dense_rows<R>(a.lin_b[blk], j, s_act, kLd, s_w, u);
+    __syncthreads();
+    dense_rows<R>(a.lin_b[blk], j, s_act, kLd, u);
     float gt[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) gt[r] = 1.f;
     if (a.gated) {
       float gp[R];
-      dense_rows<R>(a.gate[blk], j, s_in + a.n_in, kLd, s_w, gp);   // the context sits behind x in s_in
+      dense_rows<R>(a.gate[blk], j, s_in + a.n_in, kLd, gp);   // the context sits behind x in s_in
 #pragma unroll
       for (int r = 0; r < R; ++r) gt[r] = sigmoidf_(gp[r]);
     }
@@ -154,9 +171,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const MlpArgs 
   float* s_in = smem_f;
   float* s_h = s_in + R * kLd;
   float* s_act = s_h + R * kLd;
-  float* s_w = s_act + R * kLd;
   const int row0 = blockIdx.x * R, nrows = min(R, a.rows - row0);
-  mlp_trunk<R, false>(a, row0, nrows, s_in, s_h, s_act, s_w, nullptr);
+  mlp_trunk<R, false>(a, row0, nrows, s_in, s_h, s_act, nullptr);
   // final layer: output features j, j + 128, ... for this thread
   for (int j0 = 0; j0 < a.n_out; j0 += kMlpThreads) {
     MlpLayer L = a.last;
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const MlpArgs 
     L.b += j0;
     L.J = min(kMlpThreads, a.n_out - j0);
     float acc[R];
-    dense_rows<R>(L, threadIdx.x, s_h, kLd, s_w, acc);
+    dense_rows<R>(L, threadIdx.x, s_h, kLd, acc);
     if (threadIdx.x < L.J) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -208,14 +224,13 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_backward_kernel(const MlpArgs
   float* s_in = smem_f;
   float* s_h = s_in + R * kLd;
   float* s_act = s_h + R * kLd;
-  float* s_w = s_act + R * kLd;                       // kMlpChunk * kMlpThreads floats
-  float* s_keep = s_w + kMlpChunk * kMlpThreads;      // n_blocks x {h_in, t, u, gate} x [R][kLd]
+  float* s_keep = s_act + R * kLd;                    // n_blocks x {h_in, t, u, gate} x [R][kLd]
   float* s_g = s_keep + a.n_blocks * 4 * R * kLd;     // gradient vectors [R][max(n_out, kLd)]
   const int j = threadIdx.x;
   const int row0 = blockIdx.x * R, nrows = min(R, a.rows - row0);
   const int n0 = a.n_in + a.n_ctx, H = a.hidden;
-  const int g_ld = max(a.n_out, kLd);
-  mlp_trunk<R, true>(a, row0, nrows, s_in, s_h, s_act, s_w, s_keep);
+  const int g_ld = (max(a.n_out, kLd) + 3) & ~3;
+  mlp_trunk<R, true>(a, row0, nrows, s_in, s_h, s_act, s_keep);
   auto store = [&](int64_t off, int ld, int col, int r, float v) {   // workspace tensor [rows][ld]
     if (r < nrows && col < ld) a.ws[off + (int64_t)(row0 + r) * ld + col] = v;
   };
@@ -350,7 +365,8 @@ static int fill_mlp(const mflow_mlp_desc* d, const float* const* w, const float*
   return MFLOW_OK;
 }
 
-static int mlp_rows_per_cta(int64_t rows) { return rows <= 2048 ? 4 : 8; }
+// rows per CTA: few rows at small batches so that the grid covers the machine, more at large ones (weight reuse)
+static int mlp_rows_per_cta(int64_t rows) { return rows <= 512 ? 2 : (rows <= 8192 ? 4 : 8); }
 
 extern "C" MFLOW_API int64_t mflow_mlp_workspace_floats(const mflow_mlp_desc* d) {
   if (!d) return 0;
@@ -367,8 +383,9 @@ extern "C" MFLOW_API int mflow_mlp_forward(const mflow_mlp_desc* d, const float*
   a.x = x; a.x_ld = x_ld; a.x_step = x_step; a.ctx = ctx; a.ctx_ld = ctx_ld; a.out = out; a.out_ld = d->n_out;
   const int R = mlp_rows_per_cta(d->rows);
   const unsigned grid = (unsigned)((d->rows + R - 1) / R);
-  const size_t smem = (size_t)(3 * R * kLd + kMlpChunk * kMlpThreads) * sizeof(float);
-  if (R == 4) mlp_forward_kernel<4><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
+  const size_t smem = (size_t)(3 * R * kLd) * sizeof(float);
+  if (R == 2) mlp_forward_kernel<2><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
+  else if (R == 4) mlp_forward_kernel<4><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
   else mlp_forward_kernel<8><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("mlp_forward_kernel");
 }
@@ -386,19 +403,21 @@ extern "C" MFLOW_API int mflow_mlp_backward(const mflow_mlp_desc* d, const float
   const MlpWsLayout lay = mlp_ws_layout(a.rows, a.n_in, a.n_ctx, a.hidden, a.n_out, a.n_blocks, a.gated);
   MlpBwdOffsets o{};
   for (int i = 0; i < lay.n_layers; ++i) { o.a_off[i] = lay.a_off[i]; o.g_off[i] = lay.g_off[i]; }
-  const int R = 4;   // the recompute keeps 4 x blocks activation sets per row in shared memory
+  const int R = a.rows <= 512 ? 2 : 4;   // the recompute keeps 4 x blocks activation sets per row in shared memory
   const unsigned grid = (unsigned)((a.rows + R - 1) / R);
-  const int g_ld = a.n_out > kLd ? a.n_out : kLd;
-  const size_t smem = (size_t)(3 * R * kLd + kMlpChunk * kMlpThreads + a.n_blocks * 4 * R * kLd + R * g_ld) * sizeof(float);
+  const int g_ld = ((a.n_out > kLd ? a.n_out : kLd) + 3) & ~3;
+  const size_t smem = (size_t)(3 * R * kLd + a.n_blocks * 4 * R * kLd + R * g_ld) * sizeof(float);
   MFLOW_REQUIRE(smem <= 200 * 1024, "out_features too large for the fused backward");
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(mlp_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(mlp_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev] = true;
   }
-  mlp_backward_kernel<4><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a, o);
+  if (R == 2) mlp_backward_kernel<2><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a, o);
+  else mlp_backward_kernel<4><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a, o);
   if (int rc = check_launch("mlp_backward_kernel")) return rc;
   // parameter gradients of every layer in one launch
   MlpGradArgs g{};

@@ -298,12 +298,16 @@ class _WeightCache:
     def __init__(self):
         self._entries = {}
 
-    def get(self, weight, transposed, owner=None, fmt="tf32"):
+    def get(self, weight, transposed, owner=None, fmt="tf32", version=None):
         """owner: the long-lived tensor (parameter) that `weight` is a fresh view of, if any - the entry is then
-        bound to the owner, so that a new view object per call does not miss."""
+        bound to the owner, so that a new view object per call does not miss.
+        version: for weights DERIVED from parameters on every pass (the dense L / U of a wide LULinear): ``owner`` is then
+        any long-lived object (the module, plus a tag) and ``version`` a hashable built from the parameters' version
+        counters - the fresh tensor's address does not take part."""
         anchor = weight if owner is None else owner
-        key = (id(anchor), transposed, fmt)
-        ver = (weight.data_ptr(), anchor._version, tuple(weight.shape), config.cache_epoch)
+        key = (id(anchor), transposed, fmt) if version is None else (id(anchor), transposed, fmt, version[0])
+        ver = ((weight.data_ptr(), anchor._version, tuple(weight.shape), config.cache_epoch) if version is None
+               else (version, tuple(weight.shape), config.cache_epoch))
         ent = self._entries.get(key)
         if ent is None or ent[0]() is not anchor or ent[1] != ver:
             if len(self._entries) > 4096:
@@ -399,15 +403,15 @@ class _ConvTC(torch.autograd.Function):
     epilogue); weight gradient as a library call (cuDNN) for now; bias gradient a reduction."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu_in, owner=None):
+    def forward(ctx, x, weight, bias, residual, relu_in, owner=None, version=None):
         require_cuda(x, weight, bias, residual)
         x = _c(x)
         residual = None if residual is None else _c(residual)
         kernel = weight.shape[2]
         fmt = _conv_format()
         x_amax = tensor_amax(x) if fmt == "fp16" else None
-        y = _conv_tc_launch(x, _weight_cache.get(weight, False, owner, fmt), weight.shape[0], kernel, bias, residual, None, relu_in, x_amax)
-        ctx.owner, ctx.fmt, ctx.x_amax = owner, fmt, x_amax
+        y = _conv_tc_launch(x, _weight_cache.get(weight, False, owner, fmt, version), weight.shape[0], kernel, bias, residual, None, relu_in, x_amax)
+        ctx.owner, ctx.fmt, ctx.x_amax, ctx.version = owner, fmt, x_amax, version
         ctx.save_for_backward(x, weight)
         ctx.relu_in, ctx.has_bias, ctx.has_res = relu_in, bias is not None, residual is not None
         return y
@@ -420,7 +424,7 @@ class _ConvTC(torch.autograd.Function):
         kernel = weight.shape[2]
         g_amax = tensor_amax(g) if ctx.fmt == "fp16" else None   # one scale for the data and the weight gradient
         if ctx.needs_input_grad[0]:
-            gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner, ctx.fmt), weight.shape[1], kernel, None, None,
+            gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner, ctx.fmt, ctx.version), weight.shape[1], kernel, None, None,
                                  x if ctx.relu_in else None, False, g_amax)
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
@@ -434,7 +438,7 @@ class _ConvTC(torch.autograd.Function):
                                                      [False, True, False])[1]
         if want_bias and gb is None:
             gb = channel_sum(g)
-        return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None, None
+        return gx, gw, gb, (g if ctx.has_res and ctx.needs_input_grad[3] else None), None, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -559,6 +563,41 @@ class _TriSolve(torch.autograd.Function):
         return g_tri, (g_rhs if ctx.needs_input_grad[1] else None), None, None, None
 
 
+class _WideSolve(torch.autograd.Function):
+    """X = T^-1 B on plane-layout right-hand sides [n, C, w, w] with a PRECOMPUTED inverse (the triangle's parameters have
+    not changed since it was built): one 1x1 convolution on the tensor cores.  Backward: g_B = T^-T g (the same kernel with
+    the transposed inverse), g_T = -(g_B) X^T over all pixels (the weight-gradient kernel)."""
+
+    @staticmethod
+    def forward(ctx, rhs, tri, inv, upper, owner, version):
+        require_cuda(rhs, inv)
+        n = inv.shape[0]
+        fmt = _conv_format()
+        rhs = _c(rhs)
+        x_amax = tensor_amax(rhs) if fmt == "fp16" else None
+        out = _conv_tc_launch(rhs, _weight_cache.get(inv.view(n, n, 1, 1), False, owner, fmt, version), n, 1, None, None, None, False, x_amax)
+        ctx.save_for_backward(inv, out)
+        ctx.cfg = (owner, version, fmt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        inv, out = ctx.saved_tensors
+        owner, version, fmt = ctx.cfg
+        n = inv.shape[0]
+        g = _c(g)
+        g_amax = tensor_amax(g) if fmt == "fp16" else None
+        g_rhs = _conv_tc_launch(g, _weight_cache.get(inv.view(n, n, 1, 1), True, owner, fmt, version), n, 1, None, None, None, False, g_amax)
+        g_tri = None
+        if ctx.needs_input_grad[1]:
+            g_tri = -conv_wgrad_tc(g_rhs, out, 1, False).view(n, n)
+        return g_rhs, g_tri, None, None, None, None
+
+
+def wide_solve(rhs_planes, tri, inv, upper, owner, version):
+    return _WideSolve.apply(rhs_planes, tri, inv, bool(upper), owner, version)
+
+
 def tri_solve(tri, rhs, upper, unit=False, block=256):
     return _TriSolve.apply(tri, rhs, bool(upper), bool(unit), int(block))
 
@@ -576,8 +615,25 @@ def channel_sum(x):
     return out
 
 
-def conv_tc(x, weight, bias=None, residual=None, relu_in=False, weight_owner=None):
-    return _ConvTC.apply(x, weight, bias, residual, bool(relu_in), weight_owner)
+def conv_tc(x, weight, bias=None, residual=None, relu_in=False, weight_owner=None, weight_version=None):
+    return _ConvTC.apply(x, weight, bias, residual, bool(relu_in), weight_owner, weight_version)
+
+
+def rows_to_planes(t):
+    """[rows, C] -> ([n, C, w, w] with n * w * w >= rows (zero padded), meta): the batch rows become the pixels of square
+    feature maps, which is the layout the tensor-core convolution kernels take - a Linear layer is then a 1x1 convolution."""
+    rows, c = t.shape
+    w = 32 if rows > 256 else (16 if rows > 64 else (8 if rows > 16 else 4))
+    n = (rows + w * w - 1) // (w * w)
+    if n * w * w != rows:
+        t = torch.cat((t, t.new_zeros(n * w * w - rows, c)), dim=0)
+    return t.reshape(n, w * w, c).transpose(1, 2).contiguous().view(n, c, w, w), (rows, w)
+
+
+def planes_to_rows(p, meta):
+    rows, w = meta
+    n, c = p.shape[0], p.shape[1]
+    return p.view(n, c, w * w).transpose(1, 2).reshape(n * w * w, c)[:rows]
 
 
 # --------------------------------------------------------------------------------------------

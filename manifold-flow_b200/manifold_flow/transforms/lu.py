@@ -15,6 +15,7 @@ from torch.nn import init
 
 from ..b200 import ops
 from ..b200.cabi import require_cuda
+from ..b200.config import config
 from ..utils import various
 from .base import Transform
 from .fusion import MAX_FUSED_CHANNELS, VersionedCache
@@ -141,6 +142,9 @@ class LULinear(Linear):
 
             return apply_affine([self._affine_map(inverse)], inputs)
         lower, upper = self._create_lower_upper()
+        wide_tc = (self.features >= 1024 and config.conv_tensor_cores and config.conditioner_math == "fp32")
+        if wide_tc:
+            return self._apply_wide(inputs, lower, upper, inverse)
         if not inverse:  # lu.py:56-73
             outputs = F.linear(F.linear(inputs, upper), lower, self.bias)
             return outputs, self.logabsdet()
@@ -152,6 +156,53 @@ class LULinear(Linear):
             outputs = torch.linalg.solve_triangular(lower, outputs, upper=False, unitriangular=True)
             outputs = torch.linalg.solve_triangular(upper, outputs, upper=True)
         return outputs.t(), -self.logabsdet()
+
+    # ---- wide layers on the tensor-core kernels ---------------------------------------------------
+    def _param_version(self):
+        return tuple(p._version for p in self._lu_params())
+
+    def _apply_wide(self, inputs, lower, upper, inverse):
+        """LULinear(3840) of the image post-processing (architectures/image_transforms.py:240-258) on the tcgen05 kernels:
+        with the batch rows laid out as pixels, y = L (U x) + b is two 1x1 convolutions (lu.py:56-73); their data and weight
+        gradients run through the same kernels.  The inverse (lu.py:75-95) is two triangular solves: while the parameters
+        change every step they run as blocked substitutions; once the same parameters are seen again (evaluation,
+        sampling, the phases of the sequential / alternating schedules that freeze this flow) the triangles are inverted
+        once and the solves become two more 1x1 convolutions."""
+        n = self.features
+        ver = self._param_version()
+        if not inverse:
+            planes, meta = ops.rows_to_planes(inputs)
+            t = ops.conv_tc(planes, upper.view(n, n, 1, 1), None, weight_owner=self._dense_cache, weight_version=("U", ver))
+            t = ops.conv_tc(t, lower.view(n, n, 1, 1), self.bias, weight_owner=self._dense_cache, weight_version=("L", ver))
+            return ops.planes_to_rows(t, meta), self.logabsdet()
+        inv = self._wide_inverses(lower, upper, ver)
+        if inv is None:
+            outputs = (inputs - self.bias).t()
+            outputs = ops.tri_solve(lower, outputs, upper=False, unit=True)
+            outputs = ops.tri_solve(upper, outputs, upper=True)
+            return outputs.t(), -self.logabsdet()
+        inv_lower, inv_upper = inv
+        planes, meta = ops.rows_to_planes(inputs - self.bias)
+        t = ops.wide_solve(planes, lower, inv_lower, False, self._dense_cache, ("Linv", ver))
+        t = ops.wide_solve(t, upper, inv_upper, True, self._dense_cache, ("Uinv", ver))
+        return ops.planes_to_rows(t, meta), -self.logabsdet()
+
+    def _wide_inverses(self, lower, upper, ver):
+        """(L^-1, U^-1) for the current parameters, or None while they are not worth computing: the first call with a new
+        parameter version answers None (substitution), the second one inverts and caches."""
+        state = self.__dict__.setdefault("_wide_inv_state", {"seen": None, "ver": None, "inv": None})
+        key = (ver, config.cache_epoch, str(lower.device))
+        if state["ver"] == key:
+            return state["inv"]
+        if state["seen"] != key:
+            state["seen"] = key
+            return None
+        with torch.no_grad():
+            eye = torch.eye(self.features, dtype=lower.dtype, device=lower.device)
+            inv_lower = torch.linalg.solve_triangular(lower.detach(), eye, upper=False, unitriangular=True)
+            inv_upper = torch.linalg.solve_triangular(upper.detach(), eye, upper=True)
+        state["ver"], state["inv"] = key, (inv_lower, inv_upper)
+        return state["inv"]
 
     # reference spelling of the two directions
     def forward_no_cache(self, inputs, full_jacobian=False):

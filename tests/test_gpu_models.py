@@ -65,7 +65,11 @@ def test_manifold_flow_modes_match_reference(cuda_device, name):
         _, lp, u = model(xd, mode="mf-fixed-manifold", context=cd)
         torch.testing.assert_close(lp.cpu().double(), _t(GOLD[f"{name}/log_prob64"]), **_lp_tol(name))
         truth, ref32 = _t(GOLD[f"{name}/log_prob64"]), _t(GOLD[f"{name}/mf-fixed-manifold/log_prob"]).double()
-        budget = 5 * (ref32 - truth).abs() + 5e-6 * truth.abs() + 2e-4
+        # per sample: 5x the reference's own fp32 error, plus the batch-level noise floor of that error (a sample on which
+        # the reference's rounding errors happen to cancel does not make the arithmetic better conditioned: the PIE term
+        # turns 1e-6 of h_orth into 1e-2 of log_prob)
+        ref_err = (ref32 - truth).abs()
+        budget = 5 * ref_err + 3 * float(ref_err.kthvalue(max(1, int(0.9 * ref_err.numel())))[0]) + 5e-6 * truth.abs() + 2e-4
         assert torch.all((lp.cpu().double() - truth).abs() <= budget), "log_prob further from fp64 than 5x the reference's fp32 error"
         # pie == mf-fixed-manifold; encode/decode/log_prob/sample API
         assert torch.equal(model(xd, mode="pie", context=cd)[1], lp)
