@@ -23,7 +23,9 @@
 
 namespace mflow {
 
-constexpr int kMlpThreads = 128;   // one thread per hidden feature (hidden <= 128)
+constexpr int kMlpFeat = 128;      // hidden features (and output features per pass of the final layer) per CTA
+constexpr int kMlpSplit = 4;       // threads per feature: they split the reduction index and add up by warp shuffles
+constexpr int kMlpThreads = kMlpFeat * kMlpSplit;
 constexpr int kMlpMaxBlocks = 4;
 
 struct MlpLayer {
@@ -44,73 +46,89 @@ struct MlpArgs {
   float* ws;                                         // per-layer (A_l, G_l) pairs, see mlp_ws_layout
 };
 
-// dense layer for the CTA's R rows: acc[r] = bias[j] + sum_k W[j][k] act[r][k] for this thread's output feature j.
-// act: shared [R][ld] (ld % 4 == 0).  The thread walks ITS weight row with 16-byte loads (a row is a run of full 128-byte
-// lines, served by L1 after the first touch) and reads the activations as broadcast 16-byte shared loads: per four k
-// one LDG.128 + R LDS.128 feed 4R FMAs.  Rows whose length is not a multiple of 4 (the first layer: in + context
-// features; the context gates) take the scalar loop.  The caller synchronises around writes to act.
-template <int R>
-__device__ __forceinline__ void dense_rows(const MlpLayer& L, int j, const float* act, int ld, float (&acc)[R]) {
-  const float bias = (j < L.J) ? __ldg(L.b + j) : 0.f;
-#pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = bias;
-  if (j >= L.J) return;
-  const float* wr = L.w + (int64_t)j * L.K;
-  if ((L.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(act)) & 15) == 0) {
-    const float4* w4 = reinterpret_cast<const float4*>(wr);
-#pragma unroll 4
-    for (int k4 = 0; k4 < L.K / 4; ++k4) {
-      const float4 w = __ldg(w4 + k4);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4 a4 = *reinterpret_cast<const float4*>(act + r * ld + 4 * k4);
-        acc[r] = fmaf(w.x, a4.x, fmaf(w.y, a4.y, fmaf(w.z, a4.z, fmaf(w.w, a4.w, acc[r]))));
-      }
-    }
-  } else {
-    for (int k = 0; k < L.K; ++k) {
-      const float w = __ldg(wr + k);
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmaf(w, act[r * ld + k], acc[r]);
-    }
-  }
+__device__ __forceinline__ float quad_sum(float v) {   // sum over the kMlpSplit = 4 adjacent lanes of a feature
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
 }
 
-// transposed product for the backward pass: acc[r] = sum_j W[j][k] g[r][j] for this thread's INPUT feature k
-// (threads read W[j][k] for consecutive k: coalesced in the original layout); g: shared [R][ld], ld % 4 == 0
+// dense layer for the CTA's R rows: acc[r] = bias[j] + sum_k W[j][k] act[r][k] for output feature j; the four threads
+// (j, q = 0..3) of the feature take every fourth 16-byte piece of the weight row - a warp reads 8 rows x 64 contiguous
+// bytes per load - and the activations arrive as broadcast 16-byte shared loads (act: shared [R][ld], ld % 4 == 0).
+// With one thread per feature a CTA was four warps, one per scheduler, and every L1 / L2 latency of the weight stream was
+// exposed (100 us per launch at 256 rows); sixteen warps hide it.  Rows whose length is not a multiple of 4 (the first
+// layer: in + context features; the context gates) take the scalar loop.  All lanes of a warp must call (shuffles); the
+// result is valid in every lane of the quad.  The caller synchronises around writes to act.
 template <int R>
-__device__ __forceinline__ void dense_rows_t(const MlpLayer& L, int k, const float* g, int ld, float (&acc)[R]) {
+__device__ __forceinline__ void dense_rows(const MlpLayer& L, int j, int q, const float* act, int ld, float (&acc)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  if (k >= L.K) return;
-  const float* wc = L.w + k;
-  int j = 0;
+  if (j < L.J) {
+    const float* wr = L.w + (int64_t)j * L.K;
+    if ((L.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(act)) & 15) == 0) {
+      const float4* w4 = reinterpret_cast<const float4*>(wr);
 #pragma unroll 2
-  for (; j + 4 <= L.J; j += 4) {
-    const float w0 = __ldg(wc + (int64_t)j * L.K), w1 = __ldg(wc + (int64_t)(j + 1) * L.K), w2 = __ldg(wc + (int64_t)(j + 2) * L.K),
-                w3 = __ldg(wc + (int64_t)(j + 3) * L.K);
+      for (int k4 = q; k4 < L.K / 4; k4 += kMlpSplit) {
+        const float4 w = __ldg(w4 + k4);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float4 g4 = *reinterpret_cast<const float4*>(g + r * ld + j);
-      acc[r] = fmaf(w0, g4.x, fmaf(w1, g4.y, fmaf(w2, g4.z, fmaf(w3, g4.w, acc[r]))));
+        for (int r = 0; r < R; ++r) {
+          const float4 a4 = *reinterpret_cast<const float4*>(act + r * ld + 4 * k4);
+          acc[r] = fmaf(w.x, a4.x, fmaf(w.y, a4.y, fmaf(w.z, a4.z, fmaf(w.w, a4.w, acc[r]))));
+        }
+      }
+    } else {
+      for (int k = q; k < L.K; k += kMlpSplit) {
+        const float w = __ldg(wr + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(w, act[r * ld + k], acc[r]);
+      }
     }
   }
-  for (; j < L.J; ++j) {
-    const float w = __ldg(wc + (int64_t)j * L.K);
+  const float bias = (j < L.J) ? __ldg(L.b + j) : 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = fmaf(w, g[r * ld + j], acc[r]);
+  for (int r = 0; r < R; ++r) acc[r] = quad_sum(acc[r]) + bias;
+}
+
+// transposed product for the backward pass: acc[r] = sum_j W[j][k] g[r][j] for INPUT feature k; the quad's threads take
+// every fourth group of four rows j (threads read W[j][k] for consecutive k: coalesced in the original layout);
+// g: shared [R][ld], ld % 4 == 0
+template <int R>
+__device__ __forceinline__ void dense_rows_t(const MlpLayer& L, int k, int q, const float* g, int ld, float (&acc)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (k < L.K) {
+    const float* wc = L.w + k;
+    const int j_full = L.J & ~3;
+#pragma unroll 2
+    for (int j = 4 * q; j < j_full; j += 4 * kMlpSplit) {
+      const float w0 = __ldg(wc + (int64_t)j * L.K), w1 = __ldg(wc + (int64_t)(j + 1) * L.K), w2 = __ldg(wc + (int64_t)(j + 2) * L.K),
+                  w3 = __ldg(wc + (int64_t)(j + 3) * L.K);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + r * ld + j);
+        acc[r] = fmaf(w0, g4.x, fmaf(w1, g4.y, fmaf(w2, g4.z, fmaf(w3, g4.w, acc[r]))));
+      }
+    }
+    for (int j = j_full + q; j < L.J; j += kMlpSplit) {
+      const float w = __ldg(wc + (int64_t)j * L.K);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(w, g[r * ld + j], acc[r]);
+    }
   }
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = quad_sum(acc[r]);
 }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
-constexpr int kLd = kMlpThreads;   // row pitch of the shared activation arrays
+constexpr int kLd = kMlpFeat;      // row pitch of the shared activation arrays
 
 // the forward of the CTA's rows up to (not including) the final layer; optionally records the intermediates the
 // backward needs: s_keep holds, per block, {h_in, t (pre-ReLU output of lin_a), u (pre-gate output of lin_b), gate}
 template <int R, bool KEEP>
 __device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows, float* s_in, float* s_h, float* s_act, float* s_keep) {
-  const int j = threadIdx.x;
+  const int j = threadIdx.x / kMlpSplit, q = threadIdx.x % kMlpSplit;   // feature and the thread's share of its reductions
+  const bool wr = q == 0;                                                // one lane of the quad writes
   const int n0 = a.n_in + a.n_ctx;
   // inputs [x | ctx] -> shared
   for (int idx = threadIdx.x; idx < R * kLd; idx += kMlpThreads) {
@@ -124,42 +142,50 @@ __device__ __forceinline__ void mlp_trunk(const MlpArgs& a, int row0, int nrows,
   }
   float acc[R];
   __syncthreads();
-  dense_rows<R>(a.first, j, s_in, kLd, acc);
+  dense_rows<R>(a.first, j, q, s_in, kLd, acc);
+  if (wr) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) s_h[r * kLd + j] = (j < a.hidden) ? acc[r] : 0.f;
+    for (int r = 0; r < R; ++r) s_h[r * kLd + j] = (j < a.hidden) ? acc[r] : 0.f;
+  }
   for (int blk = 0; blk < a.n_blocks; ++blk) {
     float* keep = KEEP ? s_keep + blk * 4 * R * kLd : nullptr;
     __syncthreads();
+    if (wr) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float h = s_h[r * kLd + j];
-      if (KEEP) keep[r * kLd + j] = h;
-      s_act[r * kLd + j] = fmaxf(h, 0.f);
+      for (int r = 0; r < R; ++r) {
+        const float h = s_h[r * kLd + j];
+        if (KEEP) keep[r * kLd + j] = h;
+        s_act[r * kLd + j] = fmaxf(h, 0.f);
+      }
     }
     __syncthreads();
-    dense_rows<R>(a.lin_a[blk], j, s_act, kLd, acc);
+    dense_rows<R>(a.lin_a[blk], j, q, s_act, kLd, acc);
     __syncthreads();
+    if (wr) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (KEEP) keep[(R + r) * kLd + j] = acc[r];
-      s_act[r * kLd + j] = fmaxf(acc[r], 0.f);
+      for (int r = 0; r < R; ++r) {
+        if (KEEP) keep[(R + r) * kLd + j] = acc[r];
+        s_act[r * kLd + j] = fmaxf(acc[r], 0.f);
+      }
     }
     float u[R];
     __syncthreads();
-    dense_rows<R>(a.lin_b[blk], j, s_act, kLd, u);
+    dense_rows<R>(a.lin_b[blk], j, q, s_act, kLd, u);
     float gt[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) gt[r] = 1.f;
     if (a.gated) {
       float gp[R];
-      dense_rows<R>(a.gate[blk], j, s_in + a.n_in, kLd, gp);   // the context sits behind x in s_in
+      dense_rows<R>(a.gate[blk], j, q, s_in + a.n_in, kLd, gp);   // the context sits behind x in s_in
 #pragma unroll
       for (int r = 0; r < R; ++r) gt[r] = sigmoidf_(gp[r]);
     }
+    if (wr) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (KEEP) { keep[(2 * R + r) * kLd + j] = u[r]; keep[(3 * R + r) * kLd + j] = gt[r]; }
-      if (j < a.hidden) s_h[r * kLd + j] += gt[r] * u[r];
+      for (int r = 0; r < R; ++r) {
+        if (KEEP) { keep[(2 * R + r) * kLd + j] = u[r]; keep[(3 * R + r) * kLd + j] = gt[r]; }
+        if (j < a.hidden) s_h[r * kLd + j] += gt[r] * u[r];
+      }
     }
   }
   __syncthreads();
@@ -174,17 +200,18 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const MlpArgs 
   const int row0 = blockIdx.x * R, nrows = min(R, a.rows - row0);
   mlp_trunk<R, false>(a, row0, nrows, s_in, s_h, s_act, nullptr);
   // final layer: output features j, j + 128, ... for this thread
-  for (int j0 = 0; j0 < a.n_out; j0 += kMlpThreads) {
+  const int j = threadIdx.x / kMlpSplit, q = threadIdx.x % kMlpSplit;
+  for (int j0 = 0; j0 < a.n_out; j0 += kMlpFeat) {
     MlpLayer L = a.last;
     L.w += (int64_t)j0 * L.K;
     L.b += j0;
-    L.J = min(kMlpThreads, a.n_out - j0);
+    L.J = min(kMlpFeat, a.n_out - j0);
     float acc[R];
-    dense_rows<R>(L, threadIdx.x, s_h, kLd, acc);
-    if (threadIdx.x < L.J) {
+    dense_rows<R>(L, j, q, s_h, kLd, acc);
+    if (q == 0 && j < L.J) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (r < nrows) a.out[(int64_t)(row0 + r) * a.out_ld + j0 + threadIdx.x] = acc[r];
+        if (r < nrows) a.out[(int64_t)(row0 + r) * a.out_ld + j0 + j] = acc[r];
     }
   }
 }
@@ -226,7 +253,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_backward_kernel(const MlpArgs
   float* s_act = s_h + R * kLd;
   float* s_keep = s_act + R * kLd;                    // n_blocks x {h_in, t, u, gate} x [R][kLd]
   float* s_g = s_keep + a.n_blocks * 4 * R * kLd;     // gradient vectors [R][max(n_out, kLd)]
-  const int j = threadIdx.x;
+  const int j = threadIdx.x / kMlpSplit, q = threadIdx.x % kMlpSplit;
+  const bool wr = q == 0;
   const int row0 = blockIdx.x * R, nrows = min(R, a.rows - row0);
   const int n0 = a.n_in + a.n_ctx, H = a.hidden;
   const int g_ld = (max(a.n_out, kLd) + 3) & ~3;
@@ -240,42 +268,48 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_backward_kernel(const MlpArgs
     const int r = idx / a.n_out, c = idx - r * a.n_out;
     s_g[r * g_ld + c] = r < nrows ? a.g_out[(int64_t)(row0 + r) * a.n_out + c] : 0.f;
   }
+  if (wr) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) store(o.a_off[layer], H, j, r, s_h[r * kLd + j]);
+    for (int r = 0; r < R; ++r) store(o.a_off[layer], H, j, r, s_h[r * kLd + j]);
+  }
   __syncthreads();
-  float gh[R];   // gradient at the trunk state h (this thread's feature)
-  dense_rows_t<R>(a.last, j, s_g, g_ld, gh);
+  float gh[R];   // gradient at the trunk state h (this quad's feature; valid in every lane of the quad)
+  dense_rows_t<R>(a.last, j, q, s_g, g_ld, gh);
   for (int blk = a.n_blocks - 1; blk >= 0; --blk) {
     const float* keep = s_keep + blk * 4 * R * kLd;
     const int l_a = 1 + blk * (a.gated ? 3 : 2), l_b = l_a + 1, l_g = l_a + 2;
     __syncthreads();   // s_g / s_act free
     // h_out = h_in + gate * u:  g_u = gate * g_h ;  g_gatepre = g_h * u * gate * (1 - gate)
+    if (wr) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float u = keep[(2 * R + r) * kLd + j], gt = keep[(3 * R + r) * kLd + j], t = keep[(R + r) * kLd + j];
-      const float g_u = (j < H) ? gh[r] * gt : 0.f;
-      s_g[r * g_ld + j] = g_u;                                         // G_b
-      store(o.g_off[l_b], H, j, r, g_u);
-      store(o.a_off[l_b], H, j, r, fmaxf(t, 0.f));                     // A_b = relu(t)
-      if (a.gated) {
-        store(o.g_off[l_g], H, j, r, (j < H) ? gh[r] * u * gt * (1.f - gt) : 0.f);
-        if (j < a.n_ctx) store(o.a_off[l_g], a.n_ctx, j, r, s_in[r * kLd + a.n_in + j]);
+      for (int r = 0; r < R; ++r) {
+        const float u = keep[(2 * R + r) * kLd + j], gt = keep[(3 * R + r) * kLd + j], t = keep[(R + r) * kLd + j];
+        const float g_u = (j < H) ? gh[r] * gt : 0.f;
+        s_g[r * g_ld + j] = g_u;                                         // G_b
+        store(o.g_off[l_b], H, j, r, g_u);
+        store(o.a_off[l_b], H, j, r, fmaxf(t, 0.f));                     // A_b = relu(t)
+        if (a.gated) {
+          store(o.g_off[l_g], H, j, r, (j < H) ? gh[r] * u * gt * (1.f - gt) : 0.f);
+          if (j < a.n_ctx) store(o.a_off[l_g], a.n_ctx, j, r, s_in[r * kLd + a.n_in + j]);
+        }
       }
     }
     __syncthreads();
     float ga[R];
-    dense_rows_t<R>(a.lin_b[blk], j, s_g, g_ld, ga);                   // gradient at relu(t)
+    dense_rows_t<R>(a.lin_b[blk], j, q, s_g, g_ld, ga);                  // gradient at relu(t)
     __syncthreads();
+    if (wr) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float t = keep[(R + r) * kLd + j], hin = keep[r * kLd + j];
-      const float g_t = (j < H && t > 0.f) ? ga[r] : 0.f;
-      s_g[r * g_ld + j] = g_t;                                         // G_a
-      store(o.g_off[l_a], H, j, r, g_t);
-      store(o.a_off[l_a], H, j, r, fmaxf(hin, 0.f));                   // A_a = relu(h_in)
+      for (int r = 0; r < R; ++r) {
+        const float t = keep[(R + r) * kLd + j], hin = keep[r * kLd + j];
+        const float g_t = (j < H && t > 0.f) ? ga[r] : 0.f;
+        s_g[r * g_ld + j] = g_t;                                         // G_a
+        store(o.g_off[l_a], H, j, r, g_t);
+        store(o.a_off[l_a], H, j, r, fmaxf(hin, 0.f));                   // A_a = relu(h_in)
+      }
     }
     __syncthreads();
-    dense_rows_t<R>(a.lin_a[blk], j, s_g, g_ld, ga);                   // gradient at relu(h_in)
+    dense_rows_t<R>(a.lin_a[blk], j, q, s_g, g_ld, ga);                  // gradient at relu(h_in)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float hin = keep[r * kLd + j];
@@ -284,16 +318,18 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_backward_kernel(const MlpArgs
   }
   __syncthreads();
   // first layer: G = g_h0, A = [x | ctx]; g_x = (W_0^T g_h0)[:n_in]
+  if (wr) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    s_g[r * g_ld + j] = (j < H) ? gh[r] : 0.f;
-    store(o.g_off[0], H, j, r, (j < H) ? gh[r] : 0.f);
-    if (j < n0) store(o.a_off[0], n0, j, r, s_in[r * kLd + j]);
+    for (int r = 0; r < R; ++r) {
+      s_g[r * g_ld + j] = (j < H) ? gh[r] : 0.f;
+      store(o.g_off[0], H, j, r, (j < H) ? gh[r] : 0.f);
+      if (j < n0) store(o.a_off[0], n0, j, r, s_in[r * kLd + j]);
+    }
   }
   __syncthreads();
   float gx[R];
-  dense_rows_t<R>(a.first, j, s_g, g_ld, gx);
-  if (a.g_x != nullptr && j < a.n_in) {
+  dense_rows_t<R>(a.first, j, q, s_g, g_ld, gx);
+  if (wr && a.g_x != nullptr && j < a.n_in) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (r < nrows) a.g_x[(int64_t)(row0 + r) * a.n_in + j] = gx[r];
@@ -347,8 +383,8 @@ using namespace mflow;
 static int fill_mlp(const mflow_mlp_desc* d, const float* const* w, const float* const* b, MlpArgs& a) {
   MFLOW_REQUIRE(d && w && b, "null pointer");
   MFLOW_REQUIRE(d->rows >= 0 && d->n_in >= 1 && d->n_out >= 1, "bad extents");
-  MFLOW_REQUIRE(d->hidden >= 1 && d->hidden <= kMlpThreads, "hidden features must be <= 128");
-  MFLOW_REQUIRE(d->n_in + d->n_ctx <= kMlpThreads, "in_features + context_features must be <= 128");
+  MFLOW_REQUIRE(d->hidden >= 1 && d->hidden <= kMlpFeat, "hidden features must be <= 128");
+  MFLOW_REQUIRE(d->n_in + d->n_ctx <= kMlpFeat, "in_features + context_features must be <= 128");
   MFLOW_REQUIRE(d->n_blocks >= 0 && d->n_blocks <= kMlpMaxBlocks, "at most 4 residual blocks");
   a.rows = (int)d->rows; a.n_in = d->n_in; a.n_ctx = d->n_ctx; a.hidden = d->hidden; a.n_out = d->n_out;
   a.n_blocks = d->n_blocks; a.gated = d->n_ctx > 0 ? 1 : 0;

@@ -51,6 +51,7 @@ constexpr int kWgRawSlots = 3, kWgQSlots = 6;   // at most: a.n_raw (2 when the 
 struct WgradArgs {
   float* partial;   // [ks][taps][Cin][Cout]
   float* bias_partial;   // [ks][Cout] or null: per-split sums of g_y over the pixels (the bias gradient comes for free)
+  float* direct_w;       // 1x1 kernel with a single K split: the epilogue writes g_w[co][ci] itself (no reduction pass)
   int B, Cin, Cout, H, W;
   int taps;         // 9 or 1
   int relu_in;
@@ -331,9 +332,16 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         float v[32];
         tmem_ld_32x32(tmem + t_lane + t * a.n_tile + c * 32, v);
         if (ci < a.Cin) {
+          if (kTaps == 1 && a.direct_w != nullptr) {
+            // final layout [co][ci]: for a fixed output channel the warp's lanes are consecutive input channels
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < n_here) dst[c * 32 + j] = F16 ? v[j] * unscale : v[j];
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < n_here) a.direct_w[(int64_t)(q0 + c * 32 + j) * a.Cin + ci] = F16 ? v[j] * unscale : v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < n_here) dst[c * 32 + j] = F16 ? v[j] * unscale : v[j];
+          }
         }
       }
     }
@@ -527,6 +535,8 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
   MFLOW_REQUIRE((a.taps == 9 ? 3 : 1) * a.n_tile + (F16 ? 5 * kWgPCols : 4 * kWgPCols) <= 512, "accumulators do not fit in tensor memory");
   const int n_ks = wgrad_splits(d);
   a.bias_partial = g_bias ? a.partial + (int64_t)n_ks * a.taps * a.Cin * a.Cout : nullptr;
+  const bool direct = a.taps == 1 && n_ks == 1;   // nothing to reduce: the kernel writes g_w / g_bias in their final layout
+  if (direct) { a.direct_w = g_w; a.bias_partial = g_bias; }
 
   CUtensorMap mx, mg;
   {  // activations, NCHW: box {box_w, rows, 128 channels, 1 image}; lands as [channel][row][w]
@@ -565,6 +575,7 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
     else MFLOW_WGRAD_LAUNCH(4, 1);
   }
 #undef MFLOW_WGRAD_LAUNCH
+  if (direct) return check_launch(F16 ? "wgrad_split3_kernel<fp16>" : "wgrad_split3_kernel<tf32>");
   const int64_t n_out = (int64_t)a.taps * a.Cin * a.Cout;
   int64_t rblocks = (n_out + a.Cout + 31) / 32;
   const int rgrid = (int)(rblocks > 16 * kNumSMs ? 16 * kNumSMs : rblocks);

@@ -563,19 +563,72 @@ class _TriSolve(torch.autograd.Function):
         return g_tri, (g_rhs if ctx.needs_input_grad[1] else None), None, None, None
 
 
+WIDE_CHUNK = 960   # reduction length per launch of a wide Linear layer (30 pipeline steps of 32 channels)
+
+
+def _wide_product(planes, weight, transposed, bias, owner, version, fmt, amax):
+    """planes [n, K, w, w] x weight [J, K] (or weight^T when ``transposed``: planes [n, J, w, w]) -> [n, J | K, w, w] on the
+    tensor-core convolution kernel, the reduction cut into chunks of WIDE_CHUNK channels that are chained through the
+    kernel's residual input: the tensor core accumulates with truncation, so one 3840-term chain loses ~1e-5
+    relative, four 960-term chains joined by round-to-nearest adds stay at the convolution kernels' ~2e-6."""
+    n_red = weight.shape[0] if transposed else weight.shape[1]
+    n_out = weight.shape[1] if transposed else weight.shape[0]
+    out = None
+    for c0 in range(0, n_red, WIDE_CHUNK):
+        c1 = min(n_red, c0 + WIDE_CHUNK)
+        xs = _c(planes[:, c0:c1])
+        w = (weight[c0:c1, :] if transposed else weight[:, c0:c1])[:, :, None, None]
+        split = _weight_cache.get(w, transposed, owner, fmt, ((version[0], c0), version[1]))
+        out = _conv_tc_launch(xs, split, n_out, 1, bias if c0 == 0 else None, out, None, False, amax)
+    return out
+
+
+class _WideLinear(torch.autograd.Function):
+    """y = W x + b on plane-layout activations for a WIDE layer (the 3840-feature LU triangles of the image
+    post-processing, lu.py:56-73): chunked tensor-core products forward and for the data gradient, one pixels-as-K
+    weight-gradient launch.  ``owner`` / ``version`` key the cached fp16 split of the (per-pass rebuilt) dense weight."""
+
+    @staticmethod
+    def forward(ctx, planes, weight, bias, owner, version):
+        require_cuda(planes, weight, bias)
+        planes = _c(planes)
+        fmt = _conv_format()
+        x_amax = tensor_amax(planes) if fmt == "fp16" else None
+        out = _wide_product(planes, weight, False, bias, owner, version, fmt, x_amax)
+        ctx.save_for_backward(planes, weight)
+        ctx.cfg = (owner, version, fmt, x_amax, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        planes, weight = ctx.saved_tensors
+        owner, version, fmt, x_amax, has_bias = ctx.cfg
+        g = _c(g)
+        g_amax = tensor_amax(g) if fmt == "fp16" else None
+        g_x = _wide_product(g, weight, True, None, owner, version, fmt, g_amax) if ctx.needs_input_grad[0] else None
+        g_w = g_b = None
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            g_w, g_b = conv_wgrad_tc(g, planes, 1, False, with_bias=True, x_amax=x_amax, g_amax=g_amax)
+            g_w = g_w.view(weight.shape)
+        return g_x, g_w, (g_b if has_bias else None), None, None
+
+
+def wide_linear(planes, weight, bias, owner, version):
+    return _WideLinear.apply(planes, weight, bias, owner, version)
+
+
 class _WideSolve(torch.autograd.Function):
     """X = T^-1 B on plane-layout right-hand sides [n, C, w, w] with a PRECOMPUTED inverse (the triangle's parameters have
-    not changed since it was built): one 1x1 convolution on the tensor cores.  Backward: g_B = T^-T g (the same kernel with
-    the transposed inverse), g_T = -(g_B) X^T over all pixels (the weight-gradient kernel)."""
+    not changed since it was built): chunked 1x1 convolutions on the tensor cores.  Backward: g_B = T^-T g (the same
+    kernel with the transposed inverse), g_T = -(g_B) X^T over all pixels (the weight-gradient kernel)."""
 
     @staticmethod
     def forward(ctx, rhs, tri, inv, upper, owner, version):
         require_cuda(rhs, inv)
-        n = inv.shape[0]
         fmt = _conv_format()
         rhs = _c(rhs)
         x_amax = tensor_amax(rhs) if fmt == "fp16" else None
-        out = _conv_tc_launch(rhs, _weight_cache.get(inv.view(n, n, 1, 1), False, owner, fmt, version), n, 1, None, None, None, False, x_amax)
+        out = _wide_product(rhs, inv, False, None, owner, version, fmt, x_amax)
         ctx.save_for_backward(inv, out)
         ctx.cfg = (owner, version, fmt)
         return out
@@ -584,13 +637,12 @@ class _WideSolve(torch.autograd.Function):
     def backward(ctx, g):
         inv, out = ctx.saved_tensors
         owner, version, fmt = ctx.cfg
-        n = inv.shape[0]
         g = _c(g)
         g_amax = tensor_amax(g) if fmt == "fp16" else None
-        g_rhs = _conv_tc_launch(g, _weight_cache.get(inv.view(n, n, 1, 1), True, owner, fmt, version), n, 1, None, None, None, False, g_amax)
+        g_rhs = _wide_product(g, inv, True, None, owner, version, fmt, g_amax)
         g_tri = None
         if ctx.needs_input_grad[1]:
-            g_tri = -conv_wgrad_tc(g_rhs, out, 1, False).view(n, n)
+            g_tri = -conv_wgrad_tc(g_rhs, out, 1, False).view(inv.shape)
         return g_rhs, g_tri, None, None, None, None
 
 

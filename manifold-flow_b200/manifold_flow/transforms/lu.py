@@ -172,8 +172,8 @@ class LULinear(Linear):
         ver = self._param_version()
         if not inverse:
             planes, meta = ops.rows_to_planes(inputs)
-            t = ops.conv_tc(planes, upper.view(n, n, 1, 1), None, weight_owner=self._dense_cache, weight_version=("U", ver))
-            t = ops.conv_tc(t, lower.view(n, n, 1, 1), self.bias, weight_owner=self._dense_cache, weight_version=("L", ver))
+            t = ops.wide_linear(planes, upper, None, self._dense_cache, ("U", ver))
+            t = ops.wide_linear(t, lower, self.bias, self._dense_cache, ("L", ver))
             return ops.planes_to_rows(t, meta), self.logabsdet()
         inv = self._wide_inverses(lower, upper, ver)
         if inv is None:
