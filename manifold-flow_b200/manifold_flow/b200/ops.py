@@ -272,6 +272,28 @@ def _split_weight_f16(w_taps):
     return hi.contiguous(), lo.contiguous(), unscale, n_pad, k_pad
 
 
+class _AmaxPool:
+    """Zero-initialised device scalars for the kernels' published absolute maxima.  One ``torch.zeros`` launch provides
+    1024 of them (a launch per scalar was 700 fill kernels per step); a slot is handed out once and never reused, the
+    views keep their block alive for as long as a consumer (a saved backward context) holds one."""
+
+    def __init__(self):
+        self._block, self._next, self._key = None, 0, None
+
+    def take(self, device):
+        key = (device, torch.cuda.current_stream(device).cuda_stream, torch.cuda.is_current_stream_capturing())
+        if self._block is None or self._next >= self._block.numel() or self._key != key:
+            self._block, self._next, self._key = torch.zeros(1024, dtype=torch.float32, device=device), 0, key
+        self._next += 1
+        return self._block[self._next - 1 : self._next]
+
+    def reset(self):
+        self._block = None
+
+
+_amax_pool = _AmaxPool()
+
+
 def tensor_amax(x, fresh=False):
     """Device scalar holding max |x|: the operand scale of the fp16-split kernels.  Kernels of this library publish it with
     their output (attribute ``_mflow_amax`` of the tensor they return: valid for exactly that tensor object at that
@@ -279,7 +301,7 @@ def tensor_amax(x, fresh=False):
     tag = getattr(x, "_mflow_amax", None)
     if tag is not None and not fresh and tag[1] == x._version and tag[2] == x.data_ptr():
         return tag[0]
-    out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    out = _amax_pool.take(x.device)
     check(lib().mflow_absmax(ptr(x), x.numel(), ptr(out), stream()), "mflow_absmax")
     cabi.count_launch()
     x._mflow_amax = (out, x._version, x.data_ptr())
@@ -342,7 +364,7 @@ def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in, x_am
     d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=kernel, relu_in=int(relu_in), relu_out=0,
                  n_pad=n_pad, k_pad=k_pad)
     y = torch.empty((b, c_out, h, w), dtype=torch.float32, device=x.device)
-    out_amax = torch.zeros(1, dtype=torch.float32, device=x.device) if f16 else None
+    out_amax = _amax_pool.take(x.device) if f16 else None
     tok = None
     if cabi.kernel_timer:  # useful (fp32-equivalent) FLOPs: 2 * pixels * c_in * c_out * taps - NOT the three tensor passes
         tok = cabi.kernel_timer.begin(f"conv{kernel}x{kernel}[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out * kernel * kernel)

@@ -24,6 +24,7 @@ def begin_pass(model=None):
     model also groups its LU layers for batched matrix builds (``lu.LUGroup``)."""
     global _pass_id
     _pass_id += 1
+    ops._amax_pool.reset()   # a model-level pass starts on a fresh block of zeroed amax slots
     if model is not None and config.batch_lu_builds and not model.__dict__.get("_lu_groups_ready", False):
         from .lu import assign_lu_groups
 
