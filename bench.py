@@ -578,11 +578,22 @@ def run_b200(args):
                         "best_launch": {"kernel": best[1], "achieved": best[0], "frac": best[0] / hbm_peak}}
         if cms > 0:  # the dominant kernel of the image configs: tcgen05 implicit-GEMM convolution
             ach = cf / (cms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv kernel of libmflow_b200 (tcgen05 + TMA implicit-GEMM conv, split-precision operands: 3 tensor passes per useful FLOP; all launches of a step)",
+            fmt = config.conv_operand_format
+            best = max((v["bytes"] / (v["ms"] * 1e-3) / 1e12, k) for k, v in conv.items() if v["ms"] > 0)
+            roof = {"bound": "tensor",
+                    "kernel": f"conv_split3_kernel<{fmt}> of libmflow_b200 (tcgen05 + TMA implicit-GEMM convolution, error-compensated {fmt} operand split: "
+                              "3 tensor-core products per useful FLOP; all launches of a step)",
                     "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "peak_source": tc_src,
-                    "traffic": ncu.get("conv", {}).get("dram_bytes"), "share_of_step": (cms / 2) / step_ms,
-                    "passes_per_useful_flop": 3,
-                    "note": "achieved counts useful fp32-equivalent FLOPs; the tensor pipe executes 3x that"}
+                    "traffic": ncu.get("conv", {}).get("dram_bytes"),
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE level-0 3x3 launch (B=256, 100->100, 32x32; algorithmic 209.7e6) "
+                                    "from the ncu --set full capture summarised in profiles/r2_ncu_summary.md",
+                    "share_of_step": (cms / 2) / step_ms, "passes_per_useful_flop": 3,
+                    "tensor_work": {"achieved": 3 * ach, "unit": "TFLOP/s of tensor-core products", "frac_of_peak": 3 * ach / tc_peak,
+                                    "note": "what the tensor pipe executes: 3 products per useful FLOP (padding of C 100 -> 112 / K to 16 not counted)"},
+                    "best_launch": {"kernel": best[1], "achieved": best[0], "frac": best[0] / tc_peak, "tensor_work_frac": 3 * best[0] / tc_peak},
+                    "tensor_pipe_active_ncu": ncu.get("conv", {}).get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "note": "achieved counts useful fp32-equivalent FLOPs; tensor_pipe_active_ncu = sm__pipe_tensor_cycles_active (% of active cycles) of the level-0 "
+                            "3x3 launch in the committed ncu capture"}
             if wms > 0:
                 wach = wf / (wms * 1e-3) / 1e12
                 roof["wgrad"] = {"achieved": wach, "frac": wach / tc_peak, "share_of_step": (wms / 2) / step_ms}

@@ -61,7 +61,11 @@ def stall_breakdown(rep, kernel_regex):
     top = []
     for r in rows[rows.index(hdr) + 1:]:
         if len(r) != len(hdr):
+            if top:
+                break      # the next kernel's section
             continue
+        if r[ix["Source"]] == "Source":
+            break
         for h in cols:
             agg[h] += int(r[ix[h]] or 0)
         top.append((int(r[ix["# Samples"]] or 0), r[ix["Source"]].strip()))
