@@ -178,6 +178,11 @@ def require_cuda(*tensors):
             )
         if t is not None and t.dtype != torch.float32:
             raise MflowError(f"the B200 kernels compute in float32; got {t.dtype}")
+        if t is not None and t.device.index != torch.cuda.current_device():
+            # kernels launch on the current device's current stream: a tensor of another device would be an illegal
+            # address (or a silent peer access)
+            raise MflowError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: wrap the call "
+                             "in `with torch.cuda.device(tensor.device):` (the flows' public methods do this for host inputs)")
 
 
 def ptr(t):
