@@ -21,7 +21,7 @@ bias = torch.randn(100, device=dev)
 with torch.no_grad(), cabi.library_variant("ablate"):
     split = ops._weight_cache.get(w, False, None, "fp16")
     amax = [ops.tensor_amax(t) for t in xs]
-    for bits, nb, nraw, stag in ((0, 0, 0, 0), (0, 0, 0, 0)):
+    for bits, nb, nraw, stag in ((0, 0, 0, 0), (0, 5, 2, 0), (0, 6, 2, 0), (0, 8, 2, 0), (5, 8, 2, 0), (2 + 16, 8, 2, 0), (23, 8, 2, 0)):
         os.environ["MFLOW_CONV_ABLATE"] = str(bits)
         os.environ["MFLOW_CONV_STAGGER"] = str(stag)
         os.environ["MFLOW_CONV_NB"] = str(nb)
@@ -44,8 +44,8 @@ with torch.no_grad(), cabi.library_variant("ablate") as lib:
     for bits, stag in ((0, 0),):
         os.environ["MFLOW_CONV_ABLATE"] = str(bits)
         os.environ["MFLOW_CONV_STAGGER"] = str(stag)
-        os.environ["MFLOW_CONV_NB"] = "0"
-        os.environ["MFLOW_CONV_NRAW"] = "0"
+        os.environ["MFLOW_CONV_NB"] = "8"
+        os.environ["MFLOW_CONV_NRAW"] = "2"
         ops._conv_tc_launch(xs[0], split, 100, 3, bias, None, None, True, amax[0])
         torch.cuda.synchronize()
         n = B * hw * hw // 128
