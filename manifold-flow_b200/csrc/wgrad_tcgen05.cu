@@ -46,7 +46,7 @@ constexpr int kWgMaxPStages = 5;                // P stages in tensor memory: 5 
 constexpr int kWgBlockPx = 32;                 // pixels per K block
 constexpr int kWgQBytes = 128 * kWgBlockPx * 4;  // 16 KB: one Q operand tile (hi or lo), up to 128 rows
 constexpr int kWgPCols = 32;                   // TMEM columns of one P part (hi or lo): the block's 32 pixels
-constexpr int kWgRawSlots = 3, kWgQSlots = 6;   // at most: a.n_raw (2 when the boxes are large) and a.n_q (what shared memory allows) are used
+constexpr int kWgRawSlots = 4, kWgQSlots = 6;   // at most: a.n_raw (see launch_wgrad) and a.n_q (what shared memory allows) are used
 
 struct WgradArgs {
   float* partial;   // [ks][taps][Cin][Cout]
@@ -58,7 +58,7 @@ struct WgradArgs {
   int rows;         // image rows per 32-pixel block (32 / W)
   int box_w;        // raw activation box width: W + 8 (3x3, starts 4 pixels left: TMA needs 16-byte aligned starts) or W
   int raw_bytes;    // one raw activation box [images][128 ci][rows][box_w] fp32
-  int n_raw;        // raw-box ring depth (2 or 3)
+  int n_raw;        // raw-box ring depth (2, 3 or 4: see launch_wgrad)
   int n_q;          // Q-tile ring depth (3 .. kWgQSlots): the chain TMA -> split -> MMA -> slot free is ~3000 cycles long
   int n_tile;       // MMA N extent (output channels of this launch's q tile, multiple of 16, <= 128)
   int blocks_per_img;  // H * W / 32
@@ -523,7 +523,20 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
   a.rows = kWgBlockPx / W / imgs;             // rows per image in a block
   a.box_w = a.taps == 9 ? W + 8 : W;
   a.raw_bytes = imgs * 128 * a.rows * a.box_w * 4;
-  a.n_raw = a.raw_bytes > 32 * 1024 ? 2 : kWgRawSlots;
+  // Raw-box ring depth.  A transform set waits on rawp_full only for the blocks it owns, i.e. (fp16 path, and 1x1 on
+  // either path) for every other block.  mbarrier waits are by phase PARITY: a waiter that sits out one phase of a slot
+  // cannot tell "two completions ago" from "not yet".  3x3 / fp16: before a set reaches block i it has written block
+  // i - 2's items into the five-stage P ring, which needs the MMAs of block i - 3's first item, hence block i - 3's box
+  // (the previous user of the slot, owned by the OTHER set) has landed - three slots are safe.  1x1: one item per block,
+  // the stage ring only reaches back to block i - 5, so with three slots a set could pass the wait for block i on the
+  // stale parity while block i - 3's box was still in flight, release the slot early and let the producer arm the barrier
+  // twice in one phase (seen as rare hangs / launch failures of the 1x1 weight gradients at 10^5 .. 10^6 rows).  With an
+  // EVEN depth a slot always belongs to the same set, which then sees every one of its phases: 1x1 uses four slots
+  // (16 KB boxes: the Q ring keeps its five slots).
+  a.n_raw = a.raw_bytes > 32 * 1024 ? 2 : (a.taps == 1 ? 4 : 3);
+#ifdef MFLOW_WGRAD_FORCE_RAW3   // dev-only: the pre-fix ring depth, to reproduce the hazard (tools/wgrad_repeat.py)
+  a.n_raw = a.raw_bytes > 32 * 1024 ? 2 : 3;
+#endif
   a.blocks_per_img = W == 4 ? 1 : H * W / kWgBlockPx;
   a.n_blocks = W == 4 ? (B + 1) / 2 : B * a.blocks_per_img;
   a.n_dy = a.taps == 9 ? 3 : 1;

@@ -4,6 +4,7 @@ Each function is one fused launch (forward) plus one fused launch (backward); in
 float32 CUDA tensors.  Nothing here falls back to eager PyTorch: a missing library, a CPU tensor
 or an unsupported shape raises.
 """
+import contextlib
 import ctypes
 import math
 import weakref
@@ -419,6 +420,22 @@ def conv_wgrad_tc(g, x, kernel, relu_in, with_bias=False, x_amax=None, g_amax=No
     return (gw, gb) if with_bias else gw
 
 
+class _GradScope:
+    """``inputs_only``: backward functions skip parameter gradients.  ``ctx.needs_input_grad`` says whether a parameter
+    requires grad, not whether this backward call was asked for it: ``torch.autograd.grad(y, x)`` of the full-Jacobian
+    passes (transforms/base.py:batch_jacobian) would otherwise run every weight-gradient kernel D times for nothing."""
+    inputs_only = False
+
+
+@contextlib.contextmanager
+def input_grads_only():
+    prev, _GradScope.inputs_only = _GradScope.inputs_only, True
+    try:
+        yield
+    finally:
+        _GradScope.inputs_only = prev
+
+
 class _ConvTC(torch.autograd.Function):
     """y = conv2d(relu?(x), W) + b (+ residual), 3x3 pad 1 or 1x1, NCHW fp32, on the tensor cores.
     Backward: data gradient through the same kernel (transposed / flipped weights, ReLU mask fused in the
@@ -448,13 +465,14 @@ class _ConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = _conv_tc_launch(g, _weight_cache.get(weight, True, ctx.owner, ctx.fmt, ctx.version), weight.shape[1], kernel, None, None,
                                  x if ctx.relu_in else None, False, g_amax)
-        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[1] and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
+        want_w = ctx.needs_input_grad[1] and not _GradScope.inputs_only
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2] and not _GradScope.inputs_only
+        if want_w and config.conv_wgrad_tensor_cores and conv_wgrad_supported(x, weight.shape[0], kernel):
             if want_bias:   # the weight-gradient kernel sums g over the pixels on the side
                 gw, gb = conv_wgrad_tc(g, x, kernel, ctx.relu_in, with_bias=True, x_amax=ctx.x_amax, g_amax=g_amax)
             else:
                 gw = conv_wgrad_tc(g, x, kernel, ctx.relu_in, x_amax=ctx.x_amax, g_amax=g_amax)
-        elif ctx.needs_input_grad[1]:   # shapes the tensor-core kernel does not take (4x4 maps): library call
+        elif want_w:   # shapes the tensor-core kernel does not take: library call
             xin = torch.relu(x) if ctx.relu_in else x
             gw = torch.ops.aten.convolution_backward(g, xin, weight, None, [1, 1], [kernel // 2] * 2, [1, 1], False, [0, 0], 1,
                                                      [False, True, False])[1]
@@ -757,7 +775,7 @@ class _ChanMix(torch.autograd.Function):
             mat_t = mat.t().contiguous()
             check(lib().mflow_chanmix_apply(ctypes.byref(d), ptr(g_y), ptr(mat_t), None, ptr(g_x), stream()), "mflow_chanmix_apply")
             cabi.count_launch()
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])) and not _GradScope.inputs_only:
             g_mat = torch.empty_like(mat)
             g_bias = torch.empty(mat.shape[0], dtype=torch.float32, device=mat.device)
             ws = cabi.workspace("wgrad", lib().mflow_chanmix_wgrad_workspace_bytes(ctypes.byref(d)), x.device)

@@ -45,7 +45,9 @@ def _add_lad(a, b):
 def batch_jacobian(fn, inputs):
     """[B, D_out, D_in] Jacobian of a per-sample map by D_out reverse passes over the batch sum
     (the reference differentiates B * D_out scalars one by one: utils/various.py:22-45,68-87)."""
-    with torch.enable_grad():
+    from ..b200 import ops
+
+    with torch.enable_grad(), ops.input_grads_only():   # d outputs / d inputs only: no parameter-gradient kernels
         x = inputs.detach().requires_grad_(True)
         y = fn(x)
         flat = y.reshape(y.shape[0], -1)

@@ -132,6 +132,37 @@ def test_wgrad_tensor_core_matches_fp64_autograd(cuda_device, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("case", [(1024, 100, 100, 32, 1, True, 600), (256, 100, 100, 32, 1, True, 1500), (256, 2, 100, 32, 1, False, 600),
+                                  (256, 100, 192, 32, 1, False, 300), (256, 100, 100, 32, 3, True, 100), (512, 100, 100, 4, 1, True, 600)])
+def test_wgrad_repeatable_under_load(cuda_device, case):
+    """Back-to-back launches of the (deterministic) weight-gradient kernel on bench-sized inputs must all return the same
+    bits.  Regression test for the raw-box ring of the 1x1 kernels: with three slots a transform set could pass an
+    mbarrier wait on a stale phase parity (rare wrong results / hangs / launch failures in the large-batch vector
+    configurations, where ResidualNet's Linear layers run as 1x1 convolutions with relu_in)."""
+    from manifold_flow.b200 import ops
+
+    b, ci, co, hw, k, relu, reps = case
+    torch.manual_seed(3)
+    x = torch.randn(b, ci, hw, hw, device=cuda_device)
+    g = torch.randn(b, co, hw, hw, device=cuda_device)
+    first = ops.conv_wgrad_tc(g, x, k, relu)
+    bad = torch.zeros((), dtype=torch.int32, device=cuda_device)
+    for _ in range(reps):   # no host synchronisation inside the loop: the launches queue up back to back
+        bad += (ops.conv_wgrad_tc(g, x, k, relu) != first).any()
+    assert int(bad) == 0
+    # accuracy at this size: sums of up to 10^6 random-sign products cancel down to ~10^3, so the error is measured against
+    # the sum of the products' magnitudes (backward error); the tensor core's fp32 accumulator truncates, which shows up as
+    # a relative bias of ~3e-8 of that scale at 10^6 pixels
+    xin = (F.relu(x) if relu else x).double()
+    w = torch.zeros(co, ci, k, k, device=cuda_device, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, w, padding=k // 2).backward(g.double())
+    w_abs = torch.zeros(co, ci, k, k, device=cuda_device, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin.abs(), w_abs, padding=k // 2).backward(g.double().abs())
+    assert ((first.double() - w.grad).abs() / w_abs.grad.clamp_min(1e-30)).max().item() < 5e-7
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("rows,n_in,n_out,ctx", [(4096, 20, 640, None), (8192, 7, 224, 2), (1024, 33, 96, 1), (4112, 3, 23, None)])
 def test_residual_net_tensor_core_path_matches_fp64(cuda_device, rows, n_in, n_out, ctx):
     """ResidualNet (reference nn/resnet.py:43-72) through the tcgen05 convolution kernels (batch rows as pixels) against
