@@ -60,9 +60,13 @@ MFLOW_API int mflow_check_device(void);
  *   y  element  at y  + o*y_so + c*y_sc + i
  *   parameter p (0 <= p < 3K-1: K widths, K heights, K-1 derivatives) of the element at
  *              params + o*p_so + c*p_sc + p*p_sp + i*p_si
- * Two layouts are implemented:
+ * Three layouts are implemented:
  *   "planes" (image, conditioner output [B, C_t*P, H, W]): p_si == 1, p_sp == n_inner
  *   "rows"   (vector, conditioner output [B, C_t*P]):       n_inner == 1, p_sp == 1
+ *   "rows x planes" (p_hw > 0): vectors x / y [O, D] (n_inner == 1) whose parameters are the NCHW output
+ *            [O / p_hw, C_t*P, p_hw] of a ResidualNet (nn/resnet.py:43-72) that was evaluated on the convolution
+ *            kernels with the batch rows as the pixels of p_hw-pixel images: parameter p of element (o, c) at
+ *            params + ((o / p_hw) * C_t*P + c*P + p) * p_hw + o % p_hw;  p_so / p_sc / p_sp / p_si are ignored.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
   int64_t n_outer;  /* O */
@@ -79,6 +83,7 @@ typedef struct {
   /* identity part copied through by the same launch (coupling merge); n_id_chan == 0 = off.
    *   src at x + o*x_so + id_off + c*id_sc + i,  dst at y + o*y_so + id_off + c*id_sc + i */
   int64_t n_id_chan, id_off, id_sc;
+  int64_t p_hw;     /* 0, or the pixels per parameter image of the "rows x planes" layout (a power of two dividing O) */
 } mflow_rqs_desc;
 
 /* Forward or inverse evaluation.

@@ -38,6 +38,8 @@ struct RqsArgs {
   int64_t n_outer, n_chan, n_inner;
   int64_t x_so, x_sc, y_so, y_sc, p_so, p_sc, p_sp, p_si;
   int64_t n_id_chan, id_off, id_sc;
+  int64_t p_hw;        // rows x planes layout: pixels per parameter image (power of two), else 0
+  int p_hw_shift;      // log2(p_hw)
   int chunks;
   uint32_t inner_mul, inner_shift;  // e / n_inner == umulhi(e, inner_mul) >> inner_shift for 0 <= e < 2^31 (planes kernels)
   RqsConsts c;
@@ -242,6 +244,80 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// rows x planes layout: x / y are vectors [O, D] (n_inner == 1) but the parameters are the conditioner's NCHW
+// output [O / HW, C_t * P, HW] - ResidualNet evaluated on the tensor-core convolution kernels keeps its batch rows
+// as the pixels of HW-pixel images (manifold_flow/b200/conditioner.py), and transposing its [O, C_t * P] result
+// back to rows (and the parameter gradient to planes again) cost more HBM traffic than the spline itself.
+// thread = (row, channel group): consecutive threads read consecutive pixels of every parameter plane (128-byte
+// coalesced, P independent loads in flight), x / y are touched in place like in the rows kernel; a row's log-det is
+// the sum of its channel groups' partial sums in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128, kTileGroups = 2;
+
+template <int K, bool INV, bool BWD>
+__global__ void __launch_bounds__(kTileRows * kTileGroups, BWD ? 2 : 3) rqs_rowtile_kernel(const RqsArgs a) {
+  constexpr int P = 3 * K - 1;
+  __shared__ float s_lad[kTileGroups][kTileRows];
+  const int r = threadIdx.x % kTileRows, cg = threadIdx.x / kTileRows;
+  const int ct = (int)a.n_chan;
+  const int64_t o0 = (int64_t)blockIdx.x * kTileRows;
+  const int64_t o = o0 + r;
+  const bool active = o < a.n_outer;
+  float lad_acc = 0.f;
+  if (active) {
+    const int64_t img = o >> a.p_hw_shift, pix = o & (a.p_hw - 1);
+    const int64_t pbase = (img * ct * P) * a.p_hw + pix;          // feature f of this row at pbase + f * HW
+    const float* po = a.params + pbase;
+    const uint32_t hw = (uint32_t)a.p_hw;
+    const float gl_s = (BWD && a.g_lad_sample) ? a.g_lad_sample[o] : 0.f;
+    for (int ch = cg; ch < ct; ch += kTileGroups) {
+      const float* pe = po + (int64_t)ch * P * hw;
+      float p[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * hw);
+      const float v = a.x[o * a.x_so + ch * a.x_sc];
+      if (!BWD) {
+        float out, lad;
+        int bin;
+        rqs_eval<K, INV>(v, p, a.c, out, lad, bin);
+        a.y[o * a.y_so + ch * a.y_sc] = out;
+        if (a.lad_elem) a.lad_elem[o * ct + ch] = lad;
+        if (a.bins) a.bins[o * ct + ch] = bin;
+        lad_acc += lad;
+      } else {
+        const float vo = INV ? a.x_out[o * a.y_so + ch * a.y_sc] : 0.f;
+        const float g = a.g_out ? a.g_out[o * a.y_so + ch * a.y_sc] : 0.f;
+        const float gl = gl_s + (a.g_lad_elem ? a.g_lad_elem[o * ct + ch] : 0.f);
+        float g_in;
+        float* gpe = a.g_params + pbase + (int64_t)ch * P * hw;
+        rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * hw, val); });
+        a.y[o * a.x_so + ch * a.x_sc] = g_in;
+      }
+    }
+  }
+  // identity features of the tile's rows (coupling merge / its gradient)
+  const int n_rows = (int)min((int64_t)kTileRows, a.n_outer - o0);
+  for (int idx = threadIdx.x; idx < n_rows * (int)a.n_id_chan; idx += kTileRows * kTileGroups) {
+    const int s2 = idx / (int)a.n_id_chan, c2 = idx - s2 * (int)a.n_id_chan;
+    if (!BWD) {
+      a.y[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] = a.x[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc];
+    } else {
+      a.y[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc] = a.g_out ? a.g_out[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] : 0.f;
+    }
+  }
+  if (!BWD && a.lad_sample != nullptr) {
+    s_lad[cg][r] = lad_acc;
+    __syncthreads();
+    if (cg == 0 && active) {
+      float s = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < kTileGroups; ++g2) s += s_lad[g2][r];
+      a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // spline on a box [left, right] x [bottom, top] with all K+1 knot derivatives given
 // (rational_quadratic_spline, rational_quadratic.py:67-168): function-level API, one thread per element,
 // parameter rows [n, 3K+1] = [widths | heights | derivatives].
@@ -308,6 +384,8 @@ static bool fill_args(const mflow_rqs_desc* d, RqsArgs& a) {
   a.x_so = d->x_so; a.x_sc = d->x_sc; a.y_so = d->y_so; a.y_sc = d->y_sc;
   a.p_so = d->p_so; a.p_sc = d->p_sc; a.p_sp = d->p_sp; a.p_si = d->p_si;
   a.n_id_chan = d->n_id_chan; a.id_off = d->id_off; a.id_sc = d->id_sc;
+  a.p_hw = d->p_hw; a.p_hw_shift = 0;
+  while (d->p_hw > 0 && (1ll << a.p_hw_shift) < d->p_hw) ++a.p_hw_shift;
   const int K = d->num_bins;
   const double T = (double)d->tail_bound;
   RqsConsts& c = a.c;
@@ -390,6 +468,9 @@ static int validate(const mflow_rqs_desc* d) {
                 "per-sample extents must fit in 32 bits");
   MFLOW_REQUIRE((double)d->min_bin_width * d->num_bins <= 1.0, "Minimal bin width too large for the number of bins");
   MFLOW_REQUIRE((double)d->min_bin_height * d->num_bins <= 1.0, "Minimal bin height too large for the number of bins");
+  MFLOW_REQUIRE(d->p_hw >= 0 && (d->p_hw & (d->p_hw - 1)) == 0, "p_hw must be 0 or a power of two");
+  MFLOW_REQUIRE(d->p_hw == 0 || (d->n_inner == 1 && d->n_outer % d->p_hw == 0),
+                "rows x planes layout: vectors (n_inner == 1) with n_outer a multiple of p_hw");
   return MFLOW_OK;
 }
 
@@ -413,6 +494,12 @@ extern "C" MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* d, const float* x
   fill_args(d, a);
   a.x = x; a.params = params; a.y = y; a.lad_elem = lad_elem; a.lad_sample = lad_sample; a.lad_base = lad_base;
   a.bins = bins;
+  if (d->p_hw > 0) {
+    const unsigned grid = (unsigned)((d->n_outer + kTileRows - 1) / kTileRows);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, false><<<grid, kTileRows * kTileGroups, 0, st>>>(a);
+                     else rqs_rowtile_kernel<K, false, false><<<grid, kTileRows * kTileGroups, 0, st>>>(a));
+    return check_launch("rqs_rowtile_kernel");
+  }
   if (rows_fast_path(d)) {
     const int spc = kRowThreads / (int)d->n_chan;
     const unsigned grid = (unsigned)((d->n_outer + spc - 1) / spc);
@@ -457,6 +544,12 @@ extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float
   fill_args(d, a);
   a.x = x_in; a.x_out = x_out; a.params = params; a.y = g_in; a.g_out = g_out; a.g_lad_sample = g_lad_sample;
   a.g_lad_elem = g_lad_elem; a.g_params = g_params;
+  if (d->p_hw > 0) {
+    const unsigned grid = (unsigned)((d->n_outer + kTileRows - 1) / kTileRows);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, true><<<grid, kTileRows * kTileGroups, 0, st>>>(a);
+                     else rqs_rowtile_kernel<K, false, true><<<grid, kTileRows * kTileGroups, 0, st>>>(a));
+    return check_launch("rqs_rowtile_kernel(bwd)");
+  }
   if (rows_fast_path(d)) {
     const int spc = kRowThreads / (int)d->n_chan;
     const unsigned grid = (unsigned)((d->n_outer + spc - 1) / spc);

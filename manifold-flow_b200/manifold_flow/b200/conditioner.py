@@ -59,6 +59,23 @@ def residual_block_linear(x, lin0, lin1, gate_layer, context):
         return x + t
 
 
+class _PlanesOut:
+    """Set by the coupling layer around its conditioner call: ``residual_net_planes`` then returns its NCHW result
+    [rows / w^2, n_out, w, w] as it is (the spline kernel reads that layout in place, ``mflow_rqs_desc.p_hw``) instead of
+    transposing it back to [rows, n_out] - that copy, and the transposition of the parameter gradient on the way back,
+    moved more bytes than the spline itself (a quarter of the cfg3 step at 65 536 rows)."""
+    enabled = False
+
+
+@contextlib.contextmanager
+def planes_output():
+    prev, _PlanesOut.enabled = _PlanesOut.enabled, True
+    try:
+        yield
+    finally:
+        _PlanesOut.enabled = prev
+
+
 def residual_net_planes(net, inputs, context):
     """ResidualNet (nn/resnet.py:43-72) on the tensor-core convolution kernels, or None when the shape does not qualify.
 
@@ -90,6 +107,8 @@ def residual_net_planes(net, inputs, context):
         else:  # glu(cat(t, gate)) = t * sigmoid(gate)   resnet.py:38-39
             h = h + lin(t, lin1, relu_in=True) * torch.sigmoid(lin(ctx_planes, block.context_layer))
     out = lin(h, net.final_layer)
+    if _PlanesOut.enabled:
+        return out
     return out.view(out.shape[0], out.shape[1], w * w).transpose(1, 2).reshape(rows, out.shape[1])
 
 

@@ -54,7 +54,8 @@ class SplineGeometry:
 
 def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
     """Descriptor for a coupling layer on the full activation tensor ``x`` ([B, C, H, W] or [B, D],
-    contiguous) and the conditioner output ``params`` ([B, C_t*P, H, W] or [B, C_t*P], contiguous)."""
+    contiguous) and the conditioner output ``params`` ([B, C_t*P, H, W] or [B, C_t*P], contiguous - or, for vectors whose
+    conditioner ran on the convolution kernels, its NCHW output [B / hw, C_t*P, h, w]: "rows x planes")."""
     p = 3 * num_bins - 1
     d = RqsDesc()
     b = x.shape[0]
@@ -71,11 +72,12 @@ def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, diviso
     d.tail_bound, d.min_bin_width, d.min_bin_height, d.min_derivative = tail_bound, min_w, min_h, min_d
     d.wh_divisor = divisor
     d.n_id_chan, d.id_off, d.id_sc = geom.n_identity, geom.i_offset * inner, geom.i_step * inner
+    d.p_hw = params.shape[2] * params.shape[3] if (x.dim() == 2 and params.dim() == 4) else 0
     return d, geom.t_offset * inner
 
 
 def _rqs_shape(d):
-    return f"[{d.n_outer}x{d.n_chan}x{d.n_inner},K={d.num_bins}]"
+    return f"[{d.n_outer}x{d.n_chan}x{d.n_inner},K={d.num_bins}{',planes' if d.p_hw else ''}]"
 
 
 def _rqs_bytes(d, backward):
@@ -98,6 +100,10 @@ class _RqsCoupling(torch.autograd.Function):
         expected = x.shape[0] * geom.n_transform * p * (x.shape[2] * x.shape[3] if x.dim() == 4 else 1)
         if params.numel() != expected:
             raise ValueError(f"conditioner output has {params.numel()} values, expected {expected}")
+        if x.dim() == 2 and params.dim() == 4:   # rows x planes: [B / hw, C_t*P, h, w] with hw a power of two dividing B
+            hw = params.shape[2] * params.shape[3]
+            if params.shape[1] != geom.n_transform * p or hw & (hw - 1) or x.shape[0] % hw:
+                raise ValueError(f"planes-layout conditioner output {tuple(params.shape)} does not match {x.shape[0]} rows x {geom.n_transform} features")
         desc, off = _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse)
         y = torch.empty_like(x)
         lad = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)

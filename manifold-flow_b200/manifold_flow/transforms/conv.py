@@ -19,7 +19,9 @@ class OneByOneConvolution(LULinear):
         """y = W x[perm] + b  (conv.py:33-41)  /  x = (W^-1 (y - b))[inv_perm]  (:43-55)."""
         group = getattr(self, "_lu_group", None)
         if group is not None:   # all same-width 1x1 convolutions of the model at once (lu.LUGroup)
-            mat, bias, lad = group.affine_maps(inverse)
+            from .fusion import member_views
+
+            mat, bias, lad = member_views(group, "_members_inv" if inverse else "_members_fwd", group.affine_maps(inverse))
             return mat[self._lu_index], bias[self._lu_index], lad[self._lu_index]
         perm = self.permutation._permutation
         inv_perm = self.permutation._inverse_permutation

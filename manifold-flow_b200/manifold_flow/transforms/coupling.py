@@ -13,7 +13,7 @@ import warnings
 import numpy as np
 import torch
 
-from ..b200 import ops
+from ..b200 import conditioner, ops
 from ..b200.cabi import require_cuda
 from .base import Transform
 from .splines import rational_quadratic as rq
@@ -106,10 +106,16 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
     def _apply_transform(self, inputs, context, inverse):
         self._check(inputs)
         require_cuda(inputs)
-        params = self.transform_net(self._identity_view(inputs), context)
         args = (self.num_bins, self.tail_bound, self.min_bin_width, self.min_bin_height, self.min_derivative, self._divisor(), inverse)
         if self._geometry is not None:
+            if inputs.dim() == 2:
+                # a vector conditioner that runs on the convolution kernels may hand over its NCHW result as it is
+                with conditioner.planes_output():
+                    params = self.transform_net(self._identity_view(inputs), context)
+            else:
+                params = self.transform_net(self._identity_view(inputs), context)
             return ops.rqs_coupling(inputs, params, self._geometry, *args)
+        params = self.transform_net(self._identity_view(inputs), context)
         # irregular mask: pack the transformed features, run the same kernel, scatter back
         packed = torch.index_select(inputs, 1, self.transform_features)
         geom = ops.SplineGeometry(self.num_transform_features, 0, 1, 0, 0, 1)

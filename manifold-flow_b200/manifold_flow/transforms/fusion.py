@@ -37,6 +37,18 @@ def current_pass():
     return _pass_id
 
 
+def member_views(holder, slot, stacked):
+    """Per-member views of the stacked [G, ...] tensors a group cache returned, through ONE ``unbind`` per tensor.
+    ``stacked[k][i]`` is a ``select`` whose backward allocates a zero [G, ...] tensor, copies one slice and adds it to the
+    running gradient: three launches per member, map and step (297 of cfg4's launches); ``unbind``'s backward is a single
+    ``stack``.  Memoised on the identity of the cached tuple (rebuilt whenever the group cache rebuilds)."""
+    ent = holder.__dict__.get(slot)
+    if ent is None or ent[0] is not stacked:
+        ent = (stacked, tuple(t.unbind(0) for t in stacked))
+        holder.__dict__[slot] = ent
+    return ent[1]
+
+
 def _linear_capable(t, x):
     return getattr(t, "_affine_map", None) is not None and t._can_fuse(x)
 
@@ -71,7 +83,7 @@ def apply_chain(transforms, x, context, inverse):
             act, conv = (run_layers[0], run_layers[1]) if not inverse else (run_layers[1], run_layers[0])
             pairs = getattr(act, "_pair_group", None)
             if pairs is not None and getattr(act, "_pair_partner", None) is conv and pairs.ready():
-                mat, bias, lad = pairs.composed(inverse)
+                mat, bias, lad = member_views(pairs, "_members_inv" if inverse else "_members_fwd", pairs.composed(inverse))
                 maps = [(mat[act._pair_index], bias[act._pair_index], lad[act._pair_index])]
         y, lad = apply_affine(maps, x)
         run.clear()

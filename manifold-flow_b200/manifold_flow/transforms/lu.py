@@ -121,7 +121,9 @@ class LULinear(Linear):
     def _affine_map(self, inverse):
         group = getattr(self, "_lu_group", None)
         if group is not None:
-            mat, bias, lad = group.affine_maps(inverse)
+            from .fusion import member_views
+
+            mat, bias, lad = member_views(group, "_members_inv" if inverse else "_members_fwd", group.affine_maps(inverse))
             return mat[self._lu_index], bias[self._lu_index], lad[self._lu_index]
 
         def build():

@@ -34,7 +34,9 @@ class ActNorm(Transform):
     def _affine_map(self, inverse):
         group = getattr(self, "_an_group", None)
         if group is not None and group.ready():
-            mat, bias, lad = group.affine_maps(inverse)
+            from .fusion import member_views
+
+            mat, bias, lad = member_views(group, "_members_inv" if inverse else "_members_fwd", group.affine_maps(inverse))
             return mat[self._an_index], bias[self._an_index], lad[self._an_index]
         if not inverse:  # :99-116
             return torch.diag(self.scale), self.shift, torch.sum(self.log_scale)

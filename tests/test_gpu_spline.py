@@ -386,3 +386,75 @@ def test_exact_order_build_meets_1e5_wherever_the_reference_does(cuda_device, na
     # the exact build reproduces a large share of the reference's fp32 outputs bit for bit
     same = (results["exact"][0].cpu() == _t(S[f"{name}/{tag}_y"])).float().mean().item()
     assert same > 0.25, same
+
+
+@pytest.mark.parametrize("rows,d,ct,k,w", [(1024, 14, 7, 11, 32), (512, 3, 1, 8, 16), (2048 + 256, 40, 20, 11, 16), (192, 2, 1, 10, 8),
+                                           (64, 5, 2, 4, 4), (4096, 64, 32, 11, 32)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rows_x_planes_layout_equals_rows_layout(cuda_device, rows, d, ct, k, w, inverse):
+    """Vectors whose conditioner ran on the convolution kernels hand the spline their parameters as [rows / hw, C_t*P, h, w]
+    (mflow_rqs_desc.p_hw).  Per element the arithmetic is the rows kernel's, so outputs, input gradients and parameter
+    gradients are bit-identical; a row's log-det is summed over two channel groups (order differs: 1e-6)."""
+    from manifold_flow.b200 import ops
+
+    t, hidden, hw = 5.0, 100.0, w * w
+    p = 3 * k - 1
+    g = torch.Generator().manual_seed(rows + d + k)
+    x = (torch.randn(rows, d, generator=g) * (t / 2)).to(cuda_device)
+    params = (torch.randn(rows, ct * p, generator=g) * 6).to(cuda_device)
+    planes = params.view(rows // hw, hw, ct * p).transpose(1, 2).contiguous().view(rows // hw, ct * p, w, w)
+    step = 2 if 2 * ct <= d + 1 and ct > 1 else 1
+    n_id = min(d - ct, ct) if step == 2 else d - ct
+    geom = ops.SplineGeometry(ct, 0, step, n_id, 1 if step == 2 else ct, step)
+    gy = torch.randn(rows, d, generator=g).to(cuda_device)
+    gl = torch.randn(rows, generator=g).to(cuda_device)
+    outs = []
+    for par in (params, planes):
+        xd, pd = x.clone().requires_grad_(True), par.clone().requires_grad_(True)
+        y, lad = ops.rqs_coupling(xd, pd, geom, k, t, 1e-3, 1e-3, 1e-3, np.sqrt(hidden), inverse)
+        ((y * gy).sum() + (lad * gl).sum()).backward()
+        outs.append((y.detach(), lad.detach(), xd.grad, pd.grad))
+    (y0, l0, gx0, gp0), (y1, l1, gx1, gp1) = outs
+    touched = torch.zeros(d, dtype=torch.bool)
+    touched[[geom.t_offset + c * geom.t_step for c in range(ct)]] = True
+    touched[[geom.i_offset + c * geom.i_step for c in range(n_id)]] = True
+    cols = touched.to(cuda_device)
+    assert torch.equal(y0[:, cols], y1[:, cols])
+    torch.testing.assert_close(l1, l0, rtol=1e-6, atol=1e-5)
+    assert torch.equal(gx0[:, cols], gx1[:, cols])
+    gp1_rows = gp1.view(rows // hw, ct * p, hw).transpose(1, 2).reshape(rows, ct * p)
+    assert torch.equal(gp0, gp1_rows)
+
+
+def test_vector_model_planes_path_matches_fused_path(cuda_device):
+    """cfg3-shaped M-flow at 32768 rows: conditioners on the convolution kernels with the spline reading their NCHW output
+    (rows x planes) against the same model through the fused per-coupling MLP kernel (the path of the small-batch parity
+    tests): log_prob and parameter gradients agree to fp32 accuracy."""
+    import golden_util as gu
+    from manifold_flow.b200 import config, factory
+
+    torch.manual_seed(gu.SEED)
+    model = factory.create_model("cfg3").to(cuda_device)
+    model.train()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(32768, 40, generator=g).to(cuda_device)
+    c = torch.randn(32768, 2, generator=g).to(cuda_device)
+    with torch.no_grad():
+        model(x, mode="projection", context=c)
+
+    def run(min_rows):
+        prev, config.linear_tc_min_rows = config.linear_tc_min_rows, min_rows
+        try:
+            model.zero_grad(set_to_none=True)
+            lp = model(x, mode="mf-fixed-manifold", context=c)[1]
+            (-lp.mean()).backward()
+            return lp.detach(), [p.grad.clone() for p in model.parameters() if p.grad is not None]
+        finally:
+            config.linear_tc_min_rows = prev
+
+    lp_tc, g_tc = run(32768)
+    lp_mlp, g_mlp = run(1 << 40)
+    torch.testing.assert_close(lp_tc, lp_mlp, rtol=2e-5, atol=2e-3)
+    num = sum(float((a.double() - b.double()).pow(2).sum()) for a, b in zip(g_tc, g_mlp)) ** 0.5
+    den = sum(float(b.double().pow(2).sum()) for b in g_mlp) ** 0.5
+    assert num / den < 1e-4, num / den
