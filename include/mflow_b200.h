@@ -67,6 +67,9 @@ MFLOW_API int mflow_check_device(void);
  *            [O / p_hw, C_t*P, p_hw] of a ResidualNet (nn/resnet.py:43-72) that was evaluated on the convolution
  *            kernels with the batch rows as the pixels of p_hw-pixel images: parameter p of element (o, c) at
  *            params + ((o / p_hw) * C_t*P + c*P + p) * p_hw + o % p_hw;  p_so / p_sc / p_sp / p_si are ignored.
+ *            x / y (and the gradients) are dense rows of D = x_so = y_so <= 92 features and point at feature 0 of
+ *            row 0; transformed feature c sits at t_off + c*x_sc.  The launch writes whole rows of y (g_in): features
+ *            that are neither transformed nor listed as identity features are copied through as well.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
   int64_t n_outer;  /* O */
@@ -84,6 +87,7 @@ typedef struct {
    *   src at x + o*x_so + id_off + c*id_sc + i,  dst at y + o*y_so + id_off + c*id_sc + i */
   int64_t n_id_chan, id_off, id_sc;
   int64_t p_hw;     /* 0, or the pixels per parameter image of the "rows x planes" layout (a power of two dividing O) */
+  int64_t t_off;    /* "rows x planes" only: index of the first transformed feature */
 } mflow_rqs_desc;
 
 /* Forward or inverse evaluation.

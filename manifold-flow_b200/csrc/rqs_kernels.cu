@@ -39,6 +39,9 @@ struct RqsArgs {
   int64_t x_so, x_sc, y_so, y_sc, p_so, p_sc, p_sp, p_si;
   int64_t n_id_chan, id_off, id_sc;
   int64_t p_hw;        // rows x planes layout: pixels per parameter image (power of two), else 0
+  int64_t t_off;       // rows x planes layout: index of the first transformed feature
+  int tile_shift;      // rows x planes layout: log2(rows per CTA)
+  uint32_t d_mul, d_shift;   // idx / x_so as a multiply-shift (rows x planes layout)
   int p_hw_shift;      // log2(p_hw)
   int chunks;
   uint32_t inner_mul, inner_shift;  // e / n_inner == umulhi(e, inner_mul) >> inner_shift for 0 <= e < 2^31 (planes kernels)
@@ -248,21 +251,52 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
 // output [O / HW, C_t * P, HW] - ResidualNet evaluated on the tensor-core convolution kernels keeps its batch rows
 // as the pixels of HW-pixel images (manifold_flow/b200/conditioner.py), and transposing its [O, C_t * P] result
 // back to rows (and the parameter gradient to planes again) cost more HBM traffic than the spline itself.
-// thread = (row, channel group): consecutive threads read consecutive pixels of every parameter plane (128-byte
-// coalesced, P independent loads in flight), x / y are touched in place like in the rows kernel; a row's log-det is
-// the sum of its channel groups' partial sums in a fixed order.
+// thread = (row, channel group), a CTA = 32 rows x 8 groups (one warp per group): a warp reads 32 consecutive pixels of
+// every parameter plane (128-byte coalesced, P independent loads in flight per thread), and a thread handles every 8th
+// transformed feature of its row.  (First version: 128 rows x 2 groups - at 65 536 rows that is a single wave of 24 warps
+// per SM with ten elements per thread in sequence: 1.9 TB/s, latency bound, ncu: 30 % occupancy, 45 % long-scoreboard.)  The tensor the launch WRITES (y, or g_in) is the tile [128 rows, D] of
+// its source (x, or g_out) with the transformed features replaced, so the CTA stages that tile through shared memory:
+// whole rows in and out with coalesced accesses instead of 4-byte stores 4 D bytes apart (the identity features and
+// their gradient pass through on the way).  A row's log-det is the sum of its channel groups' partial sums in a
+// fixed order.  x, y, g_out, g_in point at feature 0 of row 0; transformed feature c sits at t_off + c * x_sc.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileRows = 128, kTileGroups = 2;
+constexpr int kTileThreads = 256, kTileMaxD = 92;
+// Rows per CTA (a power of two, 32 .. 256; the CTA's 256 threads are rows x channel groups): as many channel groups as
+// there are transformed features to go round (at most 8, so that a warp still reads 32 consecutive pixels of a plane),
+// fewer when the row tile would not fit 48 KB of shared memory... which cannot happen for D <= 92 at 32 rows.
+static int tile_rows_shift(int64_t n_chan, int64_t d_full) {
+  int groups = 1;
+  while (groups < 8 && groups * 2 <= n_chan) groups *= 2;
+  while (groups < 8 && (size_t)(kTileThreads / groups) * ((size_t)d_full | 1) * sizeof(float) > 48 * 1024) groups *= 2;
+  int shift = 0;
+  while ((kTileThreads / groups) >> (shift + 1)) ++shift;
+  return shift;   // log2(rows per CTA)
+}
 
 template <int K, bool INV, bool BWD>
-__global__ void __launch_bounds__(kTileRows * kTileGroups, BWD ? 2 : 3) rqs_rowtile_kernel(const RqsArgs a) {
+__global__ void __launch_bounds__(kTileThreads, BWD ? 2 : 6) rqs_rowtile_kernel(const RqsArgs a) {
   constexpr int P = 3 * K - 1;
-  __shared__ float s_lad[kTileGroups][kTileRows];
-  const int r = threadIdx.x % kTileRows, cg = threadIdx.x / kTileRows;
-  const int ct = (int)a.n_chan;
-  const int64_t o0 = (int64_t)blockIdx.x * kTileRows;
+  extern __shared__ float s_tile[];                     // [rows][DS]
+  __shared__ float s_lad[kTileThreads];                 // [group][row]
+  const int tr = 1 << a.tile_shift, groups = kTileThreads >> a.tile_shift;
+  const int r = threadIdx.x & (tr - 1), cg = threadIdx.x >> a.tile_shift;
+  const int ct = (int)a.n_chan, D = (int)a.x_so, DS = D | 1;
+  const int t_off = (int)a.t_off, x_sc = (int)a.x_sc;
+  const int64_t o0 = (int64_t)blockIdx.x * tr;
+  const int n_rows = (int)min((int64_t)tr, a.n_outer - o0);
+  {
+    // the tile's rows are one contiguous range of the source: flat, fully coalesced copy; idx -> (row, column) by a
+    // multiply-shift division
+    const float* src = BWD ? a.g_out : a.x;
+    const float* base = src ? src + o0 * D : nullptr;
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(n_rows * D); idx += kTileThreads) {
+      const uint32_t rr = fast_div(idx, a.d_mul, a.d_shift), c = idx - rr * (uint32_t)D;
+      s_tile[rr * DS + c] = base ? ldg_stream(base + idx) : 0.f;
+    }
+  }
+  __syncthreads();
   const int64_t o = o0 + r;
-  const bool active = o < a.n_outer;
+  const bool active = r < n_rows;
   float lad_acc = 0.f;
   if (active) {
     const int64_t img = o >> a.p_hw_shift, pix = o & (a.p_hw - 1);
@@ -270,50 +304,44 @@ __global__ void __launch_bounds__(kTileRows * kTileGroups, BWD ? 2 : 3) rqs_rowt
     const float* po = a.params + pbase;
     const uint32_t hw = (uint32_t)a.p_hw;
     const float gl_s = (BWD && a.g_lad_sample) ? a.g_lad_sample[o] : 0.f;
-    for (int ch = cg; ch < ct; ch += kTileGroups) {
-      const float* pe = po + (int64_t)ch * P * hw;
+    float* cell = s_tile + r * DS + t_off;
+    for (int ch = cg; ch < ct; ch += groups) {
+      const uint32_t f0 = (uint32_t)(ch * P) * hw;
       float p[P];
 #pragma unroll
-      for (int j = 0; j < P; ++j) p[j] = ldg_stream(pe + j * hw);
-      const float v = a.x[o * a.x_so + ch * a.x_sc];
+      for (int j = 0; j < P; ++j) p[j] = ldg_stream(po + f0 + j * hw);
       if (!BWD) {
         float out, lad;
         int bin;
-        rqs_eval<K, INV>(v, p, a.c, out, lad, bin);
-        a.y[o * a.y_so + ch * a.y_sc] = out;
+        rqs_eval<K, INV>(cell[ch * x_sc], p, a.c, out, lad, bin);
+        cell[ch * x_sc] = out;
         if (a.lad_elem) a.lad_elem[o * ct + ch] = lad;
         if (a.bins) a.bins[o * ct + ch] = bin;
         lad_acc += lad;
       } else {
-        const float vo = INV ? a.x_out[o * a.y_so + ch * a.y_sc] : 0.f;
-        const float g = a.g_out ? a.g_out[o * a.y_so + ch * a.y_sc] : 0.f;
+        const float v = a.x[o * D + t_off + ch * x_sc];
+        const float vo = INV ? a.x_out[o * D + t_off + ch * x_sc] : 0.f;
         const float gl = gl_s + (a.g_lad_elem ? a.g_lad_elem[o * ct + ch] : 0.f);
         float g_in;
-        float* gpe = a.g_params + pbase + (int64_t)ch * P * hw;
-        rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * hw, val); });
-        a.y[o * a.x_so + ch * a.x_sc] = g_in;
+        float* gpe = a.g_params + pbase + f0;
+        rqs_grad<K, INV>(v, vo, p, a.c, cell[ch * x_sc], gl, g_in, [&](int j, float val) { stg_stream(gpe + j * hw, val); });
+        cell[ch * x_sc] = g_in;
       }
     }
   }
-  // identity features of the tile's rows (coupling merge / its gradient)
-  const int n_rows = (int)min((int64_t)kTileRows, a.n_outer - o0);
-  for (int idx = threadIdx.x; idx < n_rows * (int)a.n_id_chan; idx += kTileRows * kTileGroups) {
-    const int s2 = idx / (int)a.n_id_chan, c2 = idx - s2 * (int)a.n_id_chan;
-    if (!BWD) {
-      a.y[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] = a.x[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc];
-    } else {
-      a.y[(o0 + s2) * a.x_so + a.id_off + c2 * a.id_sc] = a.g_out ? a.g_out[(o0 + s2) * a.y_so + a.id_off + c2 * a.id_sc] : 0.f;
+  if (!BWD && a.lad_sample != nullptr) s_lad[threadIdx.x] = lad_acc;
+  __syncthreads();
+  {
+    float* base = a.y + o0 * D;
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)(n_rows * D); idx += kTileThreads) {
+      const uint32_t rr = fast_div(idx, a.d_mul, a.d_shift), c = idx - rr * (uint32_t)D;
+      stg_stream(base + idx, s_tile[rr * DS + c]);
     }
   }
-  if (!BWD && a.lad_sample != nullptr) {
-    s_lad[cg][r] = lad_acc;
-    __syncthreads();
-    if (cg == 0 && active) {
-      float s = 0.f;
-#pragma unroll
-      for (int g2 = 0; g2 < kTileGroups; ++g2) s += s_lad[g2][r];
-      a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
-    }
+  if (!BWD && a.lad_sample != nullptr && cg == 0 && active) {
+    float s = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) s += s_lad[g2 * tr + r];   // fixed order: deterministic
+    a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
   }
 }
 
@@ -384,7 +412,7 @@ static bool fill_args(const mflow_rqs_desc* d, RqsArgs& a) {
   a.x_so = d->x_so; a.x_sc = d->x_sc; a.y_so = d->y_so; a.y_sc = d->y_sc;
   a.p_so = d->p_so; a.p_sc = d->p_sc; a.p_sp = d->p_sp; a.p_si = d->p_si;
   a.n_id_chan = d->n_id_chan; a.id_off = d->id_off; a.id_sc = d->id_sc;
-  a.p_hw = d->p_hw; a.p_hw_shift = 0;
+  a.p_hw = d->p_hw; a.t_off = d->t_off; a.p_hw_shift = 0;
   while (d->p_hw > 0 && (1ll << a.p_hw_shift) < d->p_hw) ++a.p_hw_shift;
   const int K = d->num_bins;
   const double T = (double)d->tail_bound;
@@ -402,16 +430,22 @@ static bool fill_args(const mflow_rqs_desc* d, RqsArgs& a) {
   c.divisor = d->wh_divisor;
   c.rcp_divisor = 1.0f / d->wh_divisor;
   c.use_divisor = d->wh_divisor != 1.0f;
-  // magic number for e / n_inner, e < 2^31: power of two -> shift; else ceil(2^(32+s) / d) with s = ceil(log2 d) - 1...
-  const uint64_t dv = (uint64_t)d->n_inner;
-  if ((dv & (dv - 1)) == 0) {
-    a.inner_mul = 0; a.inner_shift = 0;
-    while ((1ull << a.inner_shift) < dv) ++a.inner_shift;
-  } else {
-    uint32_t s = 0;
-    while ((1ull << s) < dv) ++s;            // s = ceil(log2 d)
-    a.inner_mul = (uint32_t)(((1ull << (31 + s)) + dv - 1) / dv);  // ceil(2^(31+s) / d) < 2^32, exact for e < 2^31
-    a.inner_shift = s - 1;
+  // magic number for e / dv, e < 2^31: power of two -> shift; else ceil(2^(32+s) / d) with s = ceil(log2 d) - 1...
+  auto magic = [](uint64_t dv, uint32_t& mul, uint32_t& shift) {
+    if ((dv & (dv - 1)) == 0) {
+      mul = 0; shift = 0;
+      while ((1ull << shift) < dv) ++shift;
+    } else {
+      uint32_t s = 0;
+      while ((1ull << s) < dv) ++s;            // s = ceil(log2 d)
+      mul = (uint32_t)(((1ull << (31 + s)) + dv - 1) / dv);  // ceil(2^(31+s) / d) < 2^32, exact for e < 2^31
+      shift = s - 1;
+    }
+  };
+  magic((uint64_t)d->n_inner, a.inner_mul, a.inner_shift);
+  if (d->p_hw > 0 && d->x_so >= 1) {
+    magic((uint64_t)d->x_so, a.d_mul, a.d_shift);
+    a.tile_shift = tile_rows_shift(d->n_chan, d->x_so);
   }
   return true;
 }
@@ -471,6 +505,9 @@ static int validate(const mflow_rqs_desc* d) {
   MFLOW_REQUIRE(d->p_hw >= 0 && (d->p_hw & (d->p_hw - 1)) == 0, "p_hw must be 0 or a power of two");
   MFLOW_REQUIRE(d->p_hw == 0 || (d->n_inner == 1 && d->n_outer % d->p_hw == 0),
                 "rows x planes layout: vectors (n_inner == 1) with n_outer a multiple of p_hw");
+  MFLOW_REQUIRE(d->p_hw == 0 || (d->x_so == d->y_so && d->x_sc == d->y_sc && d->x_so >= 1 && d->x_so <= kTileMaxD && d->t_off >= 0 &&
+                                 d->t_off + (d->n_chan - 1) * d->x_sc < d->x_so && d->n_chan * (3 * d->num_bins - 1) * d->p_hw < (1ll << 31)),
+                "rows x planes layout: dense rows of at most 92 features, x and y alike");
   return MFLOW_OK;
 }
 
@@ -495,9 +532,11 @@ extern "C" MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* d, const float* x
   a.x = x; a.params = params; a.y = y; a.lad_elem = lad_elem; a.lad_sample = lad_sample; a.lad_base = lad_base;
   a.bins = bins;
   if (d->p_hw > 0) {
-    const unsigned grid = (unsigned)((d->n_outer + kTileRows - 1) / kTileRows);
-    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, false><<<grid, kTileRows * kTileGroups, 0, st>>>(a);
-                     else rqs_rowtile_kernel<K, false, false><<<grid, kTileRows * kTileGroups, 0, st>>>(a));
+    const int64_t tile_rows = 1ll << a.tile_shift;
+    const unsigned grid = (unsigned)((d->n_outer + tile_rows - 1) / tile_rows);
+    const size_t tile_smem = (size_t)tile_rows * ((size_t)d->x_so | 1) * sizeof(float);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, false><<<grid, kTileThreads, tile_smem, st>>>(a);
+                     else rqs_rowtile_kernel<K, false, false><<<grid, kTileThreads, tile_smem, st>>>(a));
     return check_launch("rqs_rowtile_kernel");
   }
   if (rows_fast_path(d)) {
@@ -545,9 +584,11 @@ extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float
   a.x = x_in; a.x_out = x_out; a.params = params; a.y = g_in; a.g_out = g_out; a.g_lad_sample = g_lad_sample;
   a.g_lad_elem = g_lad_elem; a.g_params = g_params;
   if (d->p_hw > 0) {
-    const unsigned grid = (unsigned)((d->n_outer + kTileRows - 1) / kTileRows);
-    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, true><<<grid, kTileRows * kTileGroups, 0, st>>>(a);
-                     else rqs_rowtile_kernel<K, false, true><<<grid, kTileRows * kTileGroups, 0, st>>>(a));
+    const int64_t tile_rows = 1ll << a.tile_shift;
+    const unsigned grid = (unsigned)((d->n_outer + tile_rows - 1) / tile_rows);
+    const size_t tile_smem = (size_t)tile_rows * ((size_t)d->x_so | 1) * sizeof(float);
+    MFLOW_DISPATCH_K(d->num_bins, if (d->inverse) rqs_rowtile_kernel<K, true, true><<<grid, kTileThreads, tile_smem, st>>>(a);
+                     else rqs_rowtile_kernel<K, false, true><<<grid, kTileThreads, tile_smem, st>>>(a));
     return check_launch("rqs_rowtile_kernel(bwd)");
   }
   if (rows_fast_path(d)) {

@@ -33,7 +33,7 @@ class RqsDesc(ctypes.Structure):
         ("tail_bound", f32), ("min_bin_width", f32), ("min_bin_height", f32), ("min_derivative", f32),
         ("wh_divisor", f32),
         ("n_id_chan", i64), ("id_off", i64), ("id_sc", i64),
-        ("p_hw", i64),
+        ("p_hw", i64), ("t_off", i64),
     ]
 
 

@@ -52,6 +52,9 @@ class SplineGeometry:
         return SplineGeometry(len(transform_idx), t[0], t[1], len(identity_idx), i[0], i[1])
 
 
+ROWTILE_MAX_FEATURES = 92   # rows x planes spline layout: the kernel stages [128, D] row tiles in 48 KB of shared memory
+
+
 def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
     """Descriptor for a coupling layer on the full activation tensor ``x`` ([B, C, H, W] or [B, D],
     contiguous) and the conditioner output ``params`` ([B, C_t*P, H, W] or [B, C_t*P], contiguous - or, for vectors whose
@@ -72,7 +75,10 @@ def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, diviso
     d.tail_bound, d.min_bin_width, d.min_bin_height, d.min_derivative = tail_bound, min_w, min_h, min_d
     d.wh_divisor = divisor
     d.n_id_chan, d.id_off, d.id_sc = geom.n_identity, geom.i_offset * inner, geom.i_step * inner
-    d.p_hw = params.shape[2] * params.shape[3] if (x.dim() == 2 and params.dim() == 4) else 0
+    if x.dim() == 2 and params.dim() == 4:   # rows x planes: unshifted row pointers, the kernel stages whole rows
+        d.p_hw, d.t_off = params.shape[2] * params.shape[3], geom.t_offset
+        return d, 0
+    d.p_hw = d.t_off = 0
     return d, geom.t_offset * inner
 
 
@@ -102,7 +108,7 @@ class _RqsCoupling(torch.autograd.Function):
             raise ValueError(f"conditioner output has {params.numel()} values, expected {expected}")
         if x.dim() == 2 and params.dim() == 4:   # rows x planes: [B / hw, C_t*P, h, w] with hw a power of two dividing B
             hw = params.shape[2] * params.shape[3]
-            if params.shape[1] != geom.n_transform * p or hw & (hw - 1) or x.shape[0] % hw:
+            if params.shape[1] != geom.n_transform * p or hw & (hw - 1) or x.shape[0] % hw or x.shape[1] > ROWTILE_MAX_FEATURES:
                 raise ValueError(f"planes-layout conditioner output {tuple(params.shape)} does not match {x.shape[0]} rows x {geom.n_transform} features")
         desc, off = _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse)
         y = torch.empty_like(x)

@@ -108,7 +108,7 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
         require_cuda(inputs)
         args = (self.num_bins, self.tail_bound, self.min_bin_width, self.min_bin_height, self.min_derivative, self._divisor(), inverse)
         if self._geometry is not None:
-            if inputs.dim() == 2:
+            if inputs.dim() == 2 and inputs.shape[1] <= ops.ROWTILE_MAX_FEATURES:
                 # a vector conditioner that runs on the convolution kernels may hand over its NCHW result as it is
                 with conditioner.planes_output():
                     params = self.transform_net(self._identity_view(inputs), context)
