@@ -75,6 +75,7 @@ struct ConvArgs {
   int n_raw, n_b;         // ring depths: raw boxes, weight tiles
   int w_tile_bytes;       // one weight operand tile (hi or lo): w_rows x 128 bytes, w_rows = C_out of the tile rounded up to 8
   int tail_k8;            // the last channel block has <= 8 channels: its weight tiles travel as 32-byte rows
+  int flat;               // whole-image tiles of 8x8 / 4x4 maps: raw boxes without halo, [image][channel][H*W] (see launch_conv)
   int ring_bytes;         // weight ring (also the epilogue's staging area): max(n_b x 2 x w_tile_bytes, chunks x 16 KB)
   int aux_mode;           // 0 none, 1 residual add, 2 ReLU mask (gate)
   int aux_chunks;         // 32-channel boxes of the aux tile to fetch (0 when aux_mode == 0)
@@ -182,7 +183,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int n_raw_pre = (a.n_raw >= 2 && a.k_blocks >= 2) ? 2 : 1;
       for (int kb = 0; kb < n_raw_pre; ++kb) {
         mbar_expect_tx(&raw_full[kb], a.raw_tx);
-        tma_load_4d(s_raw + kb * a.raw_bytes, &map_x, &raw_full[kb], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+        tma_load_4d(s_raw + kb * a.raw_bytes, &map_x, &raw_full[kb], (pad && !a.flat) ? -4 : 0, a.flat ? 0 : h0 - pad, kb * kBlockK, b0);
       }
       const int n_w_pre = min(a.n_b, a.taps);
       const bool t8 = a.tail_k8 && a.k_blocks == 1;
@@ -214,7 +215,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (kb >= n_raw_pre) {
           mbar_wait(&raw_empty[rb.slot], rb.phase ^ 1);
           mbar_expect_tx(&raw_full[rb.slot], a.raw_tx);
-          tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], pad ? -4 : 0, h0 - pad, kb * kBlockK, b0);
+          tma_load_4d(s_raw + rb.slot * a.raw_bytes, &map_x, &raw_full[rb.slot], (pad && !a.flat) ? -4 : 0, a.flat ? 0 : h0 - pad, kb * kBlockK, b0);
         }
         rb.next();
       };
@@ -313,6 +314,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int pw = pm % a.W, pg = pm / a.W;
     const int phl = pg % a.rows_per_tile, pbl = pg / a.rows_per_tile;
     const int chan_stride = CS ? CS : a.box_h * a.box_w;                    // floats between channels in the raw box
+    const bool flat = CS == 0 && a.flat;   // flat boxes always take the run-time-stride instantiation: no predicate in the others
     const int raw_base = pbl * kBlockK * chan_stride + phl * a.box_w + pw;  // raw box layout [image][channel][row][w]
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     // The halves alternate pipeline steps (half h owns the TMEM stages h, h + 2, ...): two steps are in flight in
@@ -330,7 +332,11 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const float* raw = reinterpret_cast<const float*>(s_raw + rb.slot * a.raw_bytes) + raw_base;
       for (int tap = 0; tap < a.taps; ++tap, step ^= 1) {
         if (step != half) continue;
-        const float* src = raw + (pad ? (tap / 3) * a.box_w + tap % 3 + 3 : 0);
+        // halo box: the tap's pixel sits (dy, dx + 3) further in the box.  Flat box (no halo): the neighbour pixel of the
+        // same image, or zero when it lies outside the image (the convolution's padding)
+        const int dy = tap / 3, dx = tap - 3 * dy;
+        const float* src = raw + (!pad ? 0 : flat ? (dy - 1) * a.W + (dx - 1) : dy * a.box_w + dx + 3);
+        const bool ok = !(pad && flat) || ((unsigned)(phl + dy - 1) < (unsigned)a.H && (unsigned)(pw + dx - 1) < (unsigned)a.W);
         const int stage = half + 2 * my_stage;
         const uint32_t t_a = t_lane + kTileN + stage * 2 * kAPart;
         MFLOW_ST(0, kb * a.taps + tap, quad == 0 && lane == 0);
@@ -348,7 +354,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                float v0 = MFLOW_ABL(2) ? 1.f : src[(c0 + 2 * c) * chan_stride], v1 = MFLOW_ABL(2) ? 2.f : src[(c0 + 2 * c + 1) * chan_stride];
+                float v0 = MFLOW_ABL(2) ? 1.f : (ok ? src[(c0 + 2 * c) * chan_stride] : 0.f), v1 = MFLOW_ABL(2) ? 2.f : (ok ? src[(c0 + 2 * c + 1) * chan_stride] : 0.f);
                 if (a.relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                 split_f16x2(v0 * sa, v1 * sa, hi[c], lo[c]);
               }
@@ -364,7 +370,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               float hi[8], lo[8];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                float v = src[(c0 + c) * chan_stride];
+                float v = ok ? src[(c0 + c) * chan_stride] : 0.f;
                 if (a.relu_in) v = fmaxf(v, 0.f);
                 hi[c] = tf32_trunc(v);
                 lo[c] = tf32_round(v - hi[c]);
@@ -504,8 +510,14 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   a.rows_per_tile = groups < H ? groups : H;
   a.imgs_per_tile = groups / a.rows_per_tile;
   a.k_blocks = (a.Cin + kBlockK - 1) / kBlockK;
-  a.box_w = a.taps == 9 ? W + 8 : W;
-  a.box_h = a.taps == 9 ? a.rows_per_tile + 2 : a.rows_per_tile;
+  // 8x8 and 4x4 maps: a tile is a few WHOLE images.  Their halo boxes have 64- / 48-byte rows (16-byte rows for the 1x1
+  // boxes of 4x4 maps) and TMA moves a box row by row: the 4x4 halo box (1536 rows) took 11 000 cycles to arrive, four
+  // times per tile, in launches that are a single wave anyway.  Flat mode describes those tensors as [B, C, 1, H*W]: a
+  // (image, channel) plane is ONE row of 256 / 64 bytes, the box carries no halo, and the transform warps supply the
+  // zero padding themselves (a neighbour outside the image reads as 0).  Outputs and aux tiles use the same description.
+  a.flat = (a.rows_per_tile == H && W <= 8) ? 1 : 0;
+  a.box_w = (a.taps == 9 && !a.flat) ? W + 8 : W;
+  a.box_h = (a.taps == 9 && !a.flat) ? a.rows_per_tile + 2 : a.rows_per_tile;
   a.raw_tx = a.box_w * a.box_h * kBlockK * a.imgs_per_tile * 4;
   a.raw_bytes = (a.raw_tx + 1023) / 1024 * 1024;
   a.n_tile = a.Cout <= 112 ? 112 : 128;
@@ -553,23 +565,27 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
 
   CUtensorMap mx, mhi, mlo, mhi8, mlo8, maux, my;
   { const int tail = a.Cin % kBlockK; a.tail_k8 = (tail > 0 && tail <= kTailK) ? 1 : 0; }
+  // NCHW tensors as 4-D maps (W, H, C, B) - or, in flat mode, (H*W, 1, C, B): same rank and coordinates, rows of a whole plane
+  const cuuint64_t d0 = a.flat ? (cuuint64_t)H * W : (cuuint64_t)W, d1 = a.flat ? 1 : (cuuint64_t)H;
+  const cuuint64_t s1 = a.flat ? (cuuint64_t)H * W * 4 : (cuuint64_t)W * 4;
+  const cuuint32_t b0x = a.flat ? (cuuint32_t)(H * W) : (cuuint32_t)W, b1x = a.flat ? 1u : (cuuint32_t)a.rows_per_tile;
   {  // output, NCHW: box {W, rows, 32 channels, images}
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)W, (cuuint32_t)a.rows_per_tile, 32u, (cuuint32_t)a.imgs_per_tile};
+    cuuint64_t dims[4] = {d0, d1, (cuuint64_t)a.Cout, (cuuint64_t)B};
+    cuuint64_t str[3] = {s1, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
+    cuuint32_t box[4] = {b0x, b1x, 32u, (cuuint32_t)a.imgs_per_tile};
     if (!encode(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
   {  // aux (residual / gate), shaped like y: box {W, rows, 32 channels, images}
     const float* auxp = residual ? residual : (gate ? gate : y);
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cout, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)W, (cuuint32_t)a.rows_per_tile, 32u, (cuuint32_t)a.imgs_per_tile};
+    cuuint64_t dims[4] = {d0, d1, (cuuint64_t)a.Cout, (cuuint64_t)B};
+    cuuint64_t str[3] = {s1, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
+    cuuint32_t box[4] = {b0x, b1x, 32u, (cuuint32_t)a.imgs_per_tile};
     if (!encode(&maux, auxp, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
   {  // activations, NCHW: dims (W, H, C, B); box lands in shared memory as [image][channel][row][w]
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.box_h, (cuuint32_t)kBlockK, (cuuint32_t)a.imgs_per_tile};
+    cuuint64_t dims[4] = {d0, d1, (cuuint64_t)a.Cin, (cuuint64_t)B};
+    cuuint64_t str[3] = {s1, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
+    cuuint32_t box[4] = {a.flat ? b0x : (cuuint32_t)a.box_w, a.flat ? 1u : (cuuint32_t)a.box_h, (cuuint32_t)kBlockK, (cuuint32_t)a.imgs_per_tile};
     if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
   {  // weights: [taps][n_pad][k_pad], K-major swizzled tiles of w_rows x 32 channels (TF32: 128-byte rows, fp16: 64-byte rows)
@@ -599,7 +615,7 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
     }                                                                                                                      \
     conv_split3_kernel<F16, CS_><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a); \
   } while (0)
-  const int cs = a.box_w * a.box_h;
+  const int cs = a.flat ? 0 : a.box_w * a.box_h;
   if (F16 && cs == 240) MFLOW_CONV_LAUNCH(240);        // 3x3 on 32x32 and 16x16 maps
   else if (F16 && cs == 160) MFLOW_CONV_LAUNCH(160);   // 3x3 on 8x8 maps
   else if (F16 && cs == 128) MFLOW_CONV_LAUNCH(128);   // 1x1
