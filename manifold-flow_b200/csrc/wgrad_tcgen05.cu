@@ -146,7 +146,10 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(&rawp_empty[rp.slot], rp.phase ^ 1);
         MFLOW_WST(0, i, true);
         mbar_expect_tx(&rawp_full[rp.slot], a.raw_bytes);
-        tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], pad ? -4 : 0, h0 + (pad ? dy - 1 : 0), p0, b);
+        // 1x1: the block's 32 pixels of a channel are contiguous in NCHW (two whole images for 4x4 maps), and the tensor is
+        // described as [B, C, 1, H*W] - one 128-byte (64-byte) TMA row per channel instead of rows x W-float pieces
+        if (kTaps == 1) tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], r * kWgBlockPx, 0, p0, b);
+        else tma_load_4d(s_p + rp.slot * a.raw_bytes, &map_x, &rawp_full[rp.slot], -4, h0 + dy - 1, p0, b);
         mbar_wait(&q_empty[rq.slot], rq.phase ^ 1);
         MFLOW_WST(1, i, true);
         mbar_expect_tx(&qraw_full[rq.slot], a.n_tile * kWgBlockPx * 4);
@@ -325,6 +328,7 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int n_here = min(128, a.Cout - q0);
     const int n_chunks = (n_here + 31) / 32;
     const float unscale = inv_sx * inv_sg;   // exact: both are powers of two (1 on the TF32 path)
+    const bool vec4 = (a.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(a.partial) & 15) == 0;   // rows of the partials are 16-byte aligned
     for (int t = 0; t < taps_here; ++t) {
       const int tap = kTaps == 9 ? dy * 3 + t : 0;
       float* dst = a.partial + (((int64_t)ks * a.taps + tap) * a.Cin + ci) * a.Cout + q0;
@@ -337,6 +341,14 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < n_here) a.direct_w[(int64_t)(q0 + c * 32 + j) * a.Cin + ci] = F16 ? v[j] * unscale : v[j];
+          } else if (vec4) {
+            // a thread's 32 accumulator columns are 32 consecutive output channels of its row: 16-byte stores (4-byte
+            // stores 4 * Cout bytes apart were eight L2 write transactions per sector)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (c * 32 + j < n_here)
+                *reinterpret_cast<float4*>(dst + c * 32 + j) = F16 ? make_float4(v[j] * unscale, v[j + 1] * unscale, v[j + 2] * unscale, v[j + 3] * unscale)
+                                                                   : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -552,7 +564,12 @@ static int launch_wgrad(const mflow_conv_desc* d, const float* x, const float* g
   if (direct) { a.direct_w = g_w; a.bias_partial = g_bias; }
 
   CUtensorMap mx, mg;
-  {  // activations, NCHW: box {box_w, rows, 128 channels, 1 image}; lands as [channel][row][w]
+  if (a.taps == 1) {  // activations of a 1x1 convolution as [B, C, 1, H*W]: box {32 / imgs contiguous pixels, 1, 128 channels, imgs}
+    cuuint64_t dims[4] = {(cuuint64_t)H * W, 1, (cuuint64_t)a.Cin, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)(kWgBlockPx / imgs), 1u, 128u, (cuuint32_t)imgs};
+    if (!encode(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
+  } else {  // activations, NCHW: box {box_w, rows, 128 channels, imgs}; lands as [image][channel][row][w]
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a.Cin, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cin * H * W * 4};
     cuuint32_t box[4] = {(cuuint32_t)a.box_w, (cuuint32_t)a.rows, 128u, (cuuint32_t)imgs};
