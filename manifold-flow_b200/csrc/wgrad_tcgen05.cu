@@ -342,18 +342,34 @@ wgrad_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < n_here) a.direct_w[(int64_t)(q0 + c * 32 + j) * a.Cin + ci] = F16 ? v[j] * unscale : v[j];
           } else if (vec4) {
-            // a thread's 32 accumulator columns are 32 consecutive output channels of its row: 16-byte stores (4-byte
-            // stores 4 * Cout bytes apart were eight L2 write transactions per sector)
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c * 32 + j < n_here)
-                *reinterpret_cast<float4*>(dst + c * 32 + j) = F16 ? make_float4(v[j] * unscale, v[j + 1] * unscale, v[j + 2] * unscale, v[j + 3] * unscale)
-                                                                   : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            // handled below (all lanes of the warp take part)
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < n_here) dst[c * 32 + j] = F16 ? v[j] * unscale : v[j];
           }
+        }
+        if (vec4 && !(kTaps == 1 && a.direct_w != nullptr)) {
+          // The warp holds a [32 input channels (lanes)] x [32 output channels] block whose rows are 4 * Cout bytes apart
+          // in the partials: stored from the lanes directly, every store instruction touches 32 different lines (the
+          // epilogue was ~50 us of address-divergent stores per CTA with 4-byte stores, ~13 us with 16-byte ones).
+          // Through a padded shared-memory tile (the drained raw-box ring) eight lanes write one whole 128-byte row
+          // segment, four rows per instruction.
+          float* tile = reinterpret_cast<float*>(s_p) + (warp - 2) * (32 * 33);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = F16 ? v[j] * unscale : v[j];
+          __syncwarp();
+          const int rr = lane >> 3, q4 = lane & 7;
+          const int64_t row0 = ((int64_t)ks * a.taps + tap) * a.Cin + p0 + quad * 32;
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 4) {
+            const int row = r0 + rr;
+            const float* src = tile + row * 33 + 4 * q4;
+            const float4 val = make_float4(src[0], src[1], src[2], src[3]);
+            if (p0 + quad * 32 + row < a.Cin && c * 32 + 4 * q4 < n_here)
+              *reinterpret_cast<float4*>(a.partial + (row0 + row) * a.Cout + q0 + c * 32 + 4 * q4) = val;
+          }
+          __syncwarp();
         }
       }
     }
