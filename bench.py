@@ -652,6 +652,9 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
+        torch.cuda.synchronize()
+        if graph is not None and in_graph:
+            graph.reset()   # the captured NCCL kernels reference the communicator: release the graph before tearing it down
         torch.distributed.destroy_process_group()
     if rank == 0 and parity is not None and not parity["ok"]:
         sys.exit(3)

@@ -18,6 +18,7 @@ for cfg in cfg4 cfg5 cfg3; do
 done
 timeout 300 python bench.py --impl reference-gpu --config cfg4 --batch 256 --steps 3 --warmup 2 > $out/bench_cfg4_reference_gpu_b256.json 2> $out/bench_cfg4_reference_gpu_b256.err
 echo "reference-gpu cfg4 b256 rc=$?" >> $out/rc.txt
+timeout 300 python __graft_entry__.py smoke > $out/smoke.txt 2>&1; echo "smoke rc=$?" >> $out/rc.txt; tail -1 $out/smoke.txt
 if [ "$2" != "notests" ]; then
   timeout 900 python -m pytest tests -q -m gpu -x > $out/pytest_gpu.txt 2>&1
   echo "pytest rc=$?" >> $out/rc.txt
