@@ -108,10 +108,12 @@ MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* desc, const float* x, const 
  *   g_out      : gradient w.r.t. the output tensor (same indexing as y), may be NULL (= 0)
  *   g_lad_sample / g_lad_elem : gradient w.r.t. lad_sample [O] / lad_elem (either may be NULL)
  *   g_in       : gradient w.r.t. the input tensor (transform part and, if n_id_chan, identity part)
- *   g_params   : gradient w.r.t. params, same indexing as params; every entry is written */
+ *   g_params   : gradient w.r.t. params, same indexing as params; every entry is written
+ *   g_params_amax : optional device scalar (zero-initialised by the caller) that receives max |g_params| of the
+ *                launch - the operand scale of the fp16-split convolution that back-propagates it (section (b)) */
 MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* desc, const float* x_in, const float* x_out,
                        const float* params, const float* g_out, const float* g_lad_sample,
-                       const float* g_lad_elem, float* g_in, float* g_params, void* stream);
+                       const float* g_lad_elem, float* g_in, float* g_params, float* g_params_amax, void* stream);
 
 /* Spline on a box: rational_quadratic_spline(inputs, W, H, D, inverse, left, right, bottom, top, ...)
  * of manifold_flow/transforms/splines/rational_quadratic.py:67-168 - the bounded spline the unconstrained

@@ -16,8 +16,12 @@ namespace mflow {
 // ---------------------------------------------------------------------------------------------
 constexpr int kMixPix = 32;
 constexpr int kMixThreads = 128;
+constexpr int kMixFwdThreads = 256;   // chanmix_kernel: 8 warps x 4 output channels = one 32-channel pass per tile
+// pitch of the transposed matrix in shared memory: a multiple of 4 (16-byte row reads) that is 4 mod 8, so that the
+// transposing stores of 32 consecutive k hit 8 different banks instead of one (C = 64, 96)
+__host__ __device__ constexpr int mix_cp(int C) { return ((C + 3) & ~3) | 4; }
 
-__global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __restrict__ x, const float* __restrict__ mat,
+__global__ void __launch_bounds__(kMixFwdThreads) chanmix_kernel(const float* __restrict__ x, const float* __restrict__ mat,
                                                               const float* __restrict__ bias, float* __restrict__ y,
                                                               int64_t n_pix, int C, int64_t I, int64_t x_so, int64_t x_sc,
                                                               int64_t x_si, int64_t y_so, int64_t y_sc, int64_t y_si) {
@@ -26,15 +30,21 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
   // four output channels of one pixel at a time: per k one activation load and one 16-byte matrix load
   // (a broadcast) feed four FMAs.
   extern __shared__ __align__(16) float smem[];
-  const int Cp = (C + 3) & ~3;
+  const int Cp = mix_cp(C);
   float* s_matT = smem;                 // [C][Cp]
   float* s_x = smem + C * Cp;           // [C][33]
   float* s_b = s_x + C * (kMixPix + 1);  // [Cp]
-  for (int idx = threadIdx.x; idx < C * Cp; idx += kMixThreads) {
-    const int k = idx / Cp, c = idx - k * Cp;
-    s_matT[idx] = c < C ? mat[c * C + k] : 0.f;
+  // coalesced read of mat[c][k] along k, transposing store (the strided read - 32 lines per warp load, 72 rounds for a
+  // 96 x 96 matrix - was most of the 22 us a launch on a 1.5 MB activation took)
+  for (int idx = threadIdx.x; idx < C * C; idx += kMixFwdThreads) {
+    const int c = idx / C, k = idx - c * C;
+    s_matT[k * Cp + c] = mat[idx];
   }
-  for (int idx = threadIdx.x; idx < Cp; idx += kMixThreads) s_b[idx] = (bias && idx < C) ? bias[idx] : 0.f;
+  for (int idx = threadIdx.x; idx < C * (Cp - C); idx += kMixFwdThreads) {   // zero the padding columns
+    const int k = idx / (Cp - C), c = C + idx - k * (Cp - C);
+    s_matT[k * Cp + c] = 0.f;
+  }
+  for (int idx = threadIdx.x; idx < Cp; idx += kMixFwdThreads) s_b[idx] = (bias && idx < C) ? bias[idx] : 0.f;
   const bool chan_fast = (x_sc == 1);  // rows layout: channels contiguous -> walk channels fastest
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (n_pix + kMixPix - 1) / kMixPix;
@@ -43,7 +53,7 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
     const int64_t q0 = tile * kMixPix;
     const int n_here = (int)min((int64_t)kMixPix, n_pix - q0);
     __syncthreads();   // the previous tile's readers are done with s_x (and the matrix is in place)
-    for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixThreads) {
+    for (int idx = threadIdx.x; idx < C * kMixPix; idx += kMixFwdThreads) {
       int k, pq;
       if (chan_fast) { pq = idx / C; k = idx - pq * C; } else { k = idx / kMixPix; pq = idx - k * kMixPix; }
       float v = 0.f;
@@ -57,7 +67,7 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
     if (y_sc == 1) {
       // rows layout: transpose through shared memory so that stores are contiguous
       for (int c0 = 0; c0 < C; c0 += 32) {
-        for (int cc = warp * 4; cc < 32 && c0 + cc < C; cc += 16) {
+        for (int cc = warp * 4; cc < 32 && c0 + cc < C; cc += kMixFwdThreads / 8) {
           const int c = c0 + cc;
           float a0 = s_b[c], a1 = s_b[c + 1], a2 = s_b[c + 2], a3 = s_b[c + 3];
           for (int k = 0; k < C; ++k) {
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
         }
         __syncthreads();
         const int nc = min(32, C - c0);
-        for (int idx = threadIdx.x; idx < kMixPix * nc; idx += kMixThreads) {
+        for (int idx = threadIdx.x; idx < kMixPix * nc; idx += kMixFwdThreads) {
           const int pq = idx / nc, cc = idx - pq * nc;
           if (pq < n_here) {
             const int64_t q = q0 + pq, o = q / I, i = q - o * I;
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(kMixThreads) chanmix_kernel(const float* __res
     } else if (lane < n_here) {
       const int64_t q = q0 + lane, o = q / I, i = q - o * I;
       float* yq = y + o * y_so + i * y_si;
-      for (int c = warp * 4; c < C; c += 16) {
+      for (int c = warp * 4; c < C; c += kMixFwdThreads / 8) {
         float a0 = s_b[c], a1 = s_b[c + 1], a2 = s_b[c + 2], a3 = s_b[c + 3];
         for (int k = 0; k < C; ++k) {
           const float xv = s_x[k * (kMixPix + 1) + lane];
@@ -469,7 +479,7 @@ static unsigned grid_for(int64_t total, int threads) {
   return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-static size_t mix_smem(int C) { const int Cp = (C + 3) & ~3; return (size_t)(C * Cp + C * (kMixPix + 1) + Cp) * sizeof(float); }
+static size_t mix_smem(int C) { const int Cp = mix_cp(C); return (size_t)(C * Cp + C * (kMixPix + 1) + Cp) * sizeof(float); }
 static size_t wgrad_smem(int C) { return (size_t)(C * C + C + 2 * C * (kMixPix + 1)) * sizeof(float); }
 static int wgrad_grid(int64_t n_pix, int64_t n_chan) {
   // as many CTAs as pixel tiles, up to 8 per SM; the partial blocks stay below 8 MB
@@ -510,7 +520,7 @@ extern "C" MFLOW_API int mflow_chanmix_apply(const mflow_mix_desc* d, const floa
   if (smem > 48 * 1024) cudaFuncSetAttribute(chanmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t tiles = (n_pix + kMixPix - 1) / kMixPix;
   const unsigned grid = (unsigned)(tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs);   // grid-stride over the pixel tiles
-  chanmix_kernel<<<grid, kMixThreads, smem, (cudaStream_t)stream>>>(x, mat, bias, y, n_pix, C, d->n_inner, d->x_so, d->x_sc,
+  chanmix_kernel<<<grid, kMixFwdThreads, smem, (cudaStream_t)stream>>>(x, mat, bias, y, n_pix, C, d->n_inner, d->x_so, d->x_sc,
                                                                       d->x_si, d->y_so, d->y_sc, d->y_si);
   return check_launch("chanmix_kernel");
 }

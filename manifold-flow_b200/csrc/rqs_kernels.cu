@@ -35,6 +35,7 @@ struct RqsArgs {
   const float* g_lad_sample;
   const float* g_lad_elem;
   float* g_params;
+  float* g_params_amax;   // optional device scalar receiving max |g_params| of this launch
   int64_t n_outer, n_chan, n_inner;
   int64_t x_so, x_sc, y_so, y_sc, p_so, p_sc, p_sp, p_si;
   int64_t n_id_chan, id_off, id_sc;
@@ -51,6 +52,14 @@ struct RqsArgs {
 // exact unsigned division by an invariant divisor (Granlund-Montgomery, 32-bit, valid for dividends < 2^31)
 __device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t mul, uint32_t shift) {
   return mul == 0 ? (e >> shift) : (__umulhi(e, mul) >> shift);
+}
+
+// max |value| of a kernel's parameter gradients -> device scalar (zero-initialised by the caller; non-negative floats
+// order like unsigned integers): the operand scale of the fp16-split convolution that consumes them, without an extra
+// pass over the tensor.  All 32 lanes of the warp call.
+__device__ __forceinline__ void publish_amax(float* slot, float m) {
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(slot)) atomicMax(reinterpret_cast<unsigned int*>(slot), w);
 }
 
 constexpr int kPlaneThreads = 256;
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) rqs_planes_backward_kernel(c
   float* gpo = a.g_params + o * a.p_so;
   const float gl_s = a.g_lad_sample ? a.g_lad_sample[o] : 0.f;
   const uint32_t p_sp = INNER ? INNER : (uint32_t)a.p_sp;
+  float gp_max = 0.f;
   for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < per_sample; e += gridDim.x * kPlaneThreads) {
     const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
     const uint32_t poff = ch * p_sc + i * p_si;
@@ -155,9 +165,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) rqs_planes_backward_kernel(c
     float g_in;
     float* gpe = gpo + poff;
     const uint32_t sp = p_sp;
-    rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * sp, val); });
+    rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { stg_stream(gpe + j * sp, val); gp_max = fmaxf(gp_max, fabsf(val)); });
     stg_stream(gio + (ch * x_sc + i), g_in);
   }
+  if (a.g_params_amax != nullptr) publish_amax(a.g_params_amax, gp_max);
   const uint32_t n_id = (uint32_t)(a.n_id_chan * a.n_inner);
   for (uint32_t e = blockIdx.x * kPlaneThreads + threadIdx.x; e < n_id; e += gridDim.x * kPlaneThreads) {
     const uint32_t ch = INNER ? e / INNER : fast_div(e, a.inner_mul, a.inner_shift), i = e - ch * n_inner;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
   const int so = t / ct, ch = t - so * ct;
   const int64_t o = o0 + so;
   float p[P];
-  float lad = 0.f;
+  float lad = 0.f, gp_max = 0.f;
   if (active) {
 #pragma unroll
     for (int j = 0; j < P; ++j) p[j] = s_par[t * PS + j];
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
       const float gl = (a.g_lad_sample ? a.g_lad_sample[o] : 0.f) + (a.g_lad_elem ? a.g_lad_elem[o * ct + ch] : 0.f);
       float g_in;
       float* row = s_par + t * PS;  // the row is private to this thread: reuse it for the gradients
-      rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { row[j] = val; });
+      rqs_grad<K, INV>(v, vo, p, a.c, g, gl, g_in, [&](int j, float val) { row[j] = val; gp_max = fmaxf(gp_max, fabsf(val)); });
       a.y[o * a.x_so + ch * a.x_sc] = g_in;
     }
   }
@@ -237,6 +248,7 @@ __global__ void __launch_bounds__(kRowThreads) rqs_rows_kernel(const RqsArgs a, 
       a.lad_sample[o] = (a.lad_base ? a.lad_base[o] : 0.f) + s;
     }
   } else {
+    if (a.g_params_amax != nullptr) publish_amax(a.g_params_amax, gp_max);
     __syncthreads();
     float* dst = a.g_params + o0 * a.p_so;
     for (int idx = threadIdx.x; idx < total; idx += kRowThreads) {
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(kTileThreads, BWD ? 2 : 6) rqs_rowtile_kernel(
   __syncthreads();
   const int64_t o = o0 + r;
   const bool active = r < n_rows;
-  float lad_acc = 0.f;
+  float lad_acc = 0.f, gp_max = 0.f;
   if (active) {
     const int64_t img = o >> a.p_hw_shift, pix = o & (a.p_hw - 1);
     const int64_t pbase = (img * ct * P) * a.p_hw + pix;          // feature f of this row at pbase + f * HW
@@ -324,12 +336,13 @@ __global__ void __launch_bounds__(kTileThreads, BWD ? 2 : 6) rqs_rowtile_kernel(
         const float gl = gl_s + (a.g_lad_elem ? a.g_lad_elem[o * ct + ch] : 0.f);
         float g_in;
         float* gpe = a.g_params + pbase + f0;
-        rqs_grad<K, INV>(v, vo, p, a.c, cell[ch * x_sc], gl, g_in, [&](int j, float val) { stg_stream(gpe + j * hw, val); });
+        rqs_grad<K, INV>(v, vo, p, a.c, cell[ch * x_sc], gl, g_in, [&](int j, float val) { stg_stream(gpe + j * hw, val); gp_max = fmaxf(gp_max, fabsf(val)); });
         cell[ch * x_sc] = g_in;
       }
     }
   }
   if (!BWD && a.lad_sample != nullptr) s_lad[threadIdx.x] = lad_acc;
+  if (BWD && a.g_params_amax != nullptr) publish_amax(a.g_params_amax, gp_max);
   __syncthreads();
   {
     float* base = a.y + o0 * D;
@@ -573,7 +586,7 @@ extern "C" MFLOW_API int mflow_rqs_apply(const mflow_rqs_desc* d, const float* x
 
 extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float* x_in, const float* x_out, const float* params,
                                   const float* g_out, const float* g_lad_sample, const float* g_lad_elem, float* g_in,
-                                  float* g_params, void* stream) {
+                                  float* g_params, float* g_params_amax, void* stream) {
   if (int rc = validate(d)) return rc;
   if (d->n_outer == 0) return MFLOW_OK;
   MFLOW_REQUIRE(x_in && params && g_in && g_params, "null tensor pointer");
@@ -582,7 +595,7 @@ extern "C" MFLOW_API int mflow_rqs_backward(const mflow_rqs_desc* d, const float
   RqsArgs a{};
   fill_args(d, a);
   a.x = x_in; a.x_out = x_out; a.params = params; a.y = g_in; a.g_out = g_out; a.g_lad_sample = g_lad_sample;
-  a.g_lad_elem = g_lad_elem; a.g_params = g_params;
+  a.g_lad_elem = g_lad_elem; a.g_params = g_params; a.g_params_amax = g_params_amax;
   if (d->p_hw > 0) {
     const int64_t tile_rows = 1ll << a.tile_shift;
     const unsigned grid = (unsigned)((d->n_outer + tile_rows - 1) / tile_rows);

@@ -79,7 +79,7 @@ _SIGNATURES = {
     "mflow_check_device": (ctypes.c_int, []),
     "mflow_rqs_workspace_bytes": (i64, [ctypes.POINTER(RqsDesc)]),
     "mflow_rqs_apply": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
-    "mflow_rqs_backward": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 9),
+    "mflow_rqs_backward": (ctypes.c_int, [ctypes.POINTER(RqsDesc)] + [c_f32p] * 10),
     "mflow_rqs_box_apply": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 6),
     "mflow_rqs_box_backward": (ctypes.c_int, [ctypes.POINTER(RqsBoxDesc)] + [c_f32p] * 8),
     "mflow_rqs_search": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p]),

@@ -138,11 +138,16 @@ class _RqsCoupling(torch.autograd.Function):
         g_p = torch.empty_like(params)
         sh = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() + 4 * off)
         tok = cabi.kernel_timer.begin("rqs_bwd" + _rqs_shape(desc), _rqs_bytes(desc, True)) if cabi.kernel_timer else None
+        # NCHW parameters came from a tensor-core convolution, whose backward wants max |g_p| for its operand scale: the
+        # kernel publishes it on the side (one absmax pass over the largest tensor of the step less per coupling)
+        slot = _amax_pool.take(x.device) if (params.dim() == 4 and config.conv_operand_format == "fp16") else None
         check(lib().mflow_rqs_backward(ctypes.byref(desc), sh(x), sh(y), ptr(params), sh(g_y), ptr(g_lad), None, sh(g_x),
-                                       ptr(g_p), stream()), "mflow_rqs_backward")
+                                       ptr(g_p), ptr(slot), stream()), "mflow_rqs_backward")
         if tok:
             cabi.kernel_timer.end(tok)
         cabi.count_launch()
+        if slot is not None:
+            _publish_amax(g_p, slot)
         return (g_x, g_p) + (None,) * 8
 
 
@@ -185,7 +190,7 @@ class _RqsElementwise(torch.autograd.Function):
         x, params, y = ctx.saved_tensors
         g_x, g_p = torch.empty_like(x), torch.empty_like(params)
         check(lib().mflow_rqs_backward(ctypes.byref(ctx.desc), ptr(x), ptr(y), ptr(params), ptr(None if g_y is None else _c(g_y)),
-                                       None, ptr(None if g_lad is None else _c(g_lad)), ptr(g_x), ptr(g_p), stream()),
+                                       None, ptr(None if g_lad is None else _c(g_lad)), ptr(g_x), ptr(g_p), None, stream()),
               "mflow_rqs_backward")
         cabi.count_launch()
         return (g_x, g_p) + (None,) * 7
