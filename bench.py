@@ -551,7 +551,7 @@ def run_b200(args):
         for i in range(2):
             # eager, instrumented steps: give the host a head start so that the launch queue never runs dry -
             # otherwise the event pairs would also time the gaps in which the GPU waits for the next launch
-            torch.cuda._sleep(int(0.2 * 1.9e9))
+            torch.cuda._sleep(int(0.6 * 1.9e9))
             step(*dev_pool[i % len(dev_pool)])
         summ = cabi.kernel_timer.summary()
         cabi.kernel_timer = None
