@@ -1,8 +1,9 @@
 """Autograd functions over the C ABI of ``libmflow_b200.so``.
 
-Each function is one fused launch (forward) plus one fused launch (backward); inputs must be
-float32 CUDA tensors.  Nothing here falls back to eager PyTorch: a missing library, a CPU tensor
-or an unsupported shape raises.
+Each function is one fused launch (forward) plus one or two fused launches (backward); inputs must be
+float32 CUDA tensors.  There is no CPU path: a missing library or a CPU tensor raises, and so does an
+unsupported shape - with one documented exception: the weight gradient of a 3x3 convolution with more than 112
+output channels (no BASELINE configuration has one) is a cuDNN call (``_ConvTC.backward``).
 """
 import contextlib
 import ctypes

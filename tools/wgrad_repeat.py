@@ -1,6 +1,7 @@
 """Back-to-back launches of the 1x1 weight-gradient kernel (preceded by a convolution, as in the ResidualNet backward) on
 large inputs; every result must be bit-identical to the first.  With `raw3` the dev variant libmflow_b200_raw3.so (built
-with -DMFLOW_WGRAD_FORCE_RAW3: the three-slot raw ring used before the fix) runs instead, to reproduce the hazard.
+with -DMFLOW_WGRAD_FORCE_RAW3: the three-slot raw ring used before the fix; `make -C manifold-flow_b200/csrc raw3`) runs
+instead, to reproduce the hazard.
 usage: python tools/wgrad_repeat.py [raw3] [reps] [batch]"""
 import contextlib
 import os
