@@ -319,3 +319,61 @@ def test_invalidate_caches_covers_data_writes():
         invalidate_caches()
         fresh = _composed_maps(model, False)
         assert all(not torch.equal(a[0], b[0]) for a, b in zip(before, fresh))
+
+
+def test_member_views_unbind_once_and_backpropagate_like_selects():
+    """fusion.member_views hands out the members of a group's stacked maps through one unbind per tensor (memoised on
+    the cached tuple): same values and the same gradients as per-member selects, rebuilt when the cache rebuilds."""
+    from manifold_flow.transforms.fusion import member_views
+
+    class Holder:
+        pass
+
+    torch.manual_seed(1)
+    base = torch.randn(5, 3, 3, dtype=torch.float64, requires_grad=True)
+    stacked = (base * 2.0, base.sum(dim=2), base.sum(dim=(1, 2)))
+    holder = Holder()
+    views = member_views(holder, "_members_fwd", stacked)
+    assert member_views(holder, "_members_fwd", stacked) is views            # memoised on the tuple's identity
+    weights = torch.randn(5, dtype=torch.float64)
+    loss = sum(w * (views[0][i].sum() + views[1][i].sum() + views[2][i]) for i, w in enumerate(weights))
+    (g_unbind,) = torch.autograd.grad(loss, base, retain_graph=True)
+    loss_sel = sum(w * (stacked[0][i].sum() + stacked[1][i].sum() + stacked[2][i]) for i, w in enumerate(weights))
+    (g_select,) = torch.autograd.grad(loss_sel, base)
+    assert torch.equal(views[0][2], stacked[0][2]) and torch.allclose(g_unbind, g_select, atol=1e-14)
+    rebuilt = (base * 3.0, base.sum(dim=2), base.sum(dim=(1, 2)))
+    assert member_views(holder, "_members_fwd", rebuilt) is not views
+
+
+def test_scoped_switches_restore_their_state():
+    """ops.input_grads_only (full-Jacobian passes skip parameter gradients) and conditioner.planes_output (a coupling
+    layer accepts its conditioner's NCHW result) are scoped: nested use and exceptions restore the previous state."""
+    from manifold_flow.b200 import conditioner, ops
+
+    assert not ops._GradScope.inputs_only and not conditioner._PlanesOut.enabled
+    with ops.input_grads_only():
+        assert ops._GradScope.inputs_only
+        with ops.input_grads_only():
+            assert ops._GradScope.inputs_only
+        assert ops._GradScope.inputs_only
+    assert not ops._GradScope.inputs_only
+    with pytest.raises(RuntimeError):
+        with conditioner.planes_output():
+            assert conditioner._PlanesOut.enabled
+            raise RuntimeError("boom")
+    assert not conditioner._PlanesOut.enabled
+
+
+def test_rows_x_planes_descriptor_fields():
+    """The spline descriptor of a vector coupling whose parameters arrive as [rows / hw, C_t * P, h, w]: unshifted row
+    pointers (offset 0), p_hw = h * w and t_off = the first transformed feature; the rows layout keeps p_hw = 0."""
+    from manifold_flow.b200 import ops
+
+    geom = ops.SplineGeometry(7, 1, 2, 7, 0, 2)
+    x = torch.zeros(2048, 14)
+    rows = torch.zeros(2048, 7 * 32)
+    planes = torch.zeros(2, 7 * 32, 32, 32)
+    d, off = ops._rqs_desc(x, rows, geom, 11, 10.0, 1e-3, 1e-3, 1e-3, 10.0, False)
+    assert (d.p_hw, d.t_off, off) == (0, 0, 1) and d.n_outer == 2048 and d.n_chan == 7
+    d, off = ops._rqs_desc(x, planes, geom, 11, 10.0, 1e-3, 1e-3, 1e-3, 10.0, False)
+    assert (d.p_hw, d.t_off, off) == (1024, 1, 0) and d.x_so == 14 and d.x_sc == 2
