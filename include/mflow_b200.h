@@ -190,6 +190,17 @@ MFLOW_API int mflow_logtanh_apply(const float* x, float* y, float* lad_sample, i
 MFLOW_API int mflow_logtanh_backward(const float* x, const float* g_y, const float* g_lad_sample, float* g_x,
                            int64_t rows, int64_t n, int32_t inverse, float cut_point, void* stream);
 
+/* Gated residual of a ResidualBlock with context, manifold_flow/nn/resnet.py:36-40:
+ *   out = h + t * sigmoid(g)          (F.glu(cat(t, g)) = t * sigmoid(g), then the skip connection)
+ * for the large-batch vector conditioners that run on the convolution kernels (h, t, g: same shape, n floats, n % 4 == 0,
+ * 16-byte aligned).  Backward: g_h = g_out (nothing to compute), g_t = g_out * sigmoid(g), g_g = g_out * t * s (1 - s).
+ * The optional *_amax device scalars (zero on entry) receive the absolute maxima of the written tensors: the operand
+ * scales of the fp16-split convolutions that consume them. */
+MFLOW_API int mflow_glu_residual(const float* h, const float* t, const float* g, float* out, float* out_amax, int64_t n,
+                       void* stream);
+MFLOW_API int mflow_glu_residual_backward(const float* t, const float* g, const float* g_out, float* g_t, float* g_g,
+                                float* g_t_amax, float* g_g_amax, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (b') Vector conditioner: the whole ResidualNet (manifold_flow/nn/resnet.py:9-72) in one launch.
  *   h = W_0 [x | ctx] + b_0;  per block: h += gate * (W_b relu(W_a relu(h) + b_a) + b_b),

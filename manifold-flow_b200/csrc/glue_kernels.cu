@@ -728,3 +728,85 @@ extern "C" MFLOW_API int mflow_jtj_logdet(const float* jac, float* logdet, int64
                                                                                                                 rows, d, n);
   return check_launch("jtj_logdet_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Gated residual of a ResidualBlock with context (nn/resnet.py:36-40): glu(cat(t, g)) = t * sigmoid(g), out = h + that.
+// The large-batch vector conditioners (ResidualNet on the convolution kernels) ran it as sigmoid / mul / add launches
+// forward and five more backward, each a round trip of a [rows, 100] activation, plus an absmax pass for the next
+// convolution's operand scale: one launch each way here, with the absolute maxima published on the side.
+// ---------------------------------------------------------------------------------------------
+namespace mflow {
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ float absmax4(float m, const float4& v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+__device__ __forceinline__ void publish_max(float* slot, float m) {   // all lanes call; slot zero-initialised by the caller
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(slot)) atomicMax(reinterpret_cast<unsigned int*>(slot), w);
+}
+
+__global__ void __launch_bounds__(256) glu_residual_kernel(const float4* __restrict__ h, const float4* __restrict__ t,
+                                                           const float4* __restrict__ g, float4* __restrict__ out, float* out_amax,
+                                                           int64_t n4) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 hv = ldg_stream4(h + i), tv = ldg_stream4(t + i), gv = ldg_stream4(g + i);
+    float4 o;
+    o.x = hv.x + tv.x * sigmoidf_(gv.x); o.y = hv.y + tv.y * sigmoidf_(gv.y);
+    o.z = hv.z + tv.z * sigmoidf_(gv.z); o.w = hv.w + tv.w * sigmoidf_(gv.w);
+    out[i] = o;
+    m = absmax4(m, o);
+  }
+  if (out_amax != nullptr) publish_max(out_amax, m);
+}
+
+__global__ void __launch_bounds__(256) glu_residual_backward_kernel(const float4* __restrict__ t, const float4* __restrict__ g,
+                                                                    const float4* __restrict__ go, float4* __restrict__ g_t,
+                                                                    float4* __restrict__ g_g, float* g_t_amax, float* g_g_amax,
+                                                                    int64_t n4) {
+  float mt = 0.f, mg = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 tv = ldg_stream4(t + i), gv = ldg_stream4(g + i), ov = ldg_stream4(go + i);
+    const float sx = sigmoidf_(gv.x), sy = sigmoidf_(gv.y), sz = sigmoidf_(gv.z), sw = sigmoidf_(gv.w);
+    const float4 dt = make_float4(ov.x * sx, ov.y * sy, ov.z * sz, ov.w * sw);
+    // d sigmoid = s (1 - s), in the order torch's sigmoid_backward evaluates it: grad * ((1 - s) * s)
+    const float4 dg = make_float4((ov.x * tv.x) * ((1.f - sx) * sx), (ov.y * tv.y) * ((1.f - sy) * sy),
+                                  (ov.z * tv.z) * ((1.f - sz) * sz), (ov.w * tv.w) * ((1.f - sw) * sw));
+    g_t[i] = dt;
+    g_g[i] = dg;
+    mt = absmax4(mt, dt);
+    mg = absmax4(mg, dg);
+  }
+  if (g_t_amax != nullptr) publish_max(g_t_amax, mt);
+  if (g_g_amax != nullptr) publish_max(g_g_amax, mg);
+}
+}  // namespace mflow
+
+static unsigned glu_grid(int64_t n4) {
+  int64_t b = (n4 + 255) / 256;
+  if (b > 8 * kNumSMs) b = 8 * kNumSMs;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+extern "C" MFLOW_API int mflow_glu_residual(const float* h, const float* t, const float* g, float* out, float* out_amax, int64_t n,
+                                            void* stream) {
+  MFLOW_REQUIRE(h && t && g && out && n >= 0, "null pointer");
+  MFLOW_REQUIRE((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(g) |
+                                  reinterpret_cast<uintptr_t>(out)) & 15) == 0, "n must be a multiple of 4 and the tensors 16-byte aligned");
+  if (n == 0) return MFLOW_OK;
+  glu_residual_kernel<<<glu_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)h, (const float4*)t, (const float4*)g, (float4*)out,
+                                                                          out_amax, n / 4);
+  return check_launch("glu_residual_kernel");
+}
+
+extern "C" MFLOW_API int mflow_glu_residual_backward(const float* t, const float* g, const float* g_out, float* g_t, float* g_g,
+                                                     float* g_t_amax, float* g_g_amax, int64_t n, void* stream) {
+  MFLOW_REQUIRE(t && g && g_out && g_t && g_g && n >= 0, "null pointer");
+  MFLOW_REQUIRE((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(g_out) |
+                                  reinterpret_cast<uintptr_t>(g_t) | reinterpret_cast<uintptr_t>(g_g)) & 15) == 0,
+                "n must be a multiple of 4 and the tensors 16-byte aligned");
+  if (n == 0) return MFLOW_OK;
+  glu_residual_backward_kernel<<<glu_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)t, (const float4*)g, (const float4*)g_out,
+                                                                                   (float4*)g_t, (float4*)g_g, g_t_amax, g_g_amax, n / 4);
+  return check_launch("glu_residual_backward_kernel");
+}

@@ -105,7 +105,7 @@ def residual_net_planes(net, inputs, context):
         if context is None:
             h = lin(t, lin1, relu_in=True, residual=h)
         else:  # glu(cat(t, gate)) = t * sigmoid(gate)   resnet.py:38-39
-            h = h + lin(t, lin1, relu_in=True) * torch.sigmoid(lin(ctx_planes, block.context_layer))
+            h = ops.glu_residual(h, lin(t, lin1, relu_in=True), lin(ctx_planes, block.context_layer))
     out = lin(h, net.final_layer)
     if _PlanesOut.enabled:
         return out

@@ -563,6 +563,45 @@ def residual_net_fused(net, inputs, context):
     return _MlpFused.apply(inputs, context, len(layers), len(net.blocks), *params)
 
 
+class _GluResidual(torch.autograd.Function):
+    """out = h + t * sigmoid(g): the gated residual of a ResidualBlock with context (nn/resnet.py:36-40) in one launch each
+    way; the absolute maxima of the results ride along for the fp16-split convolutions that consume them."""
+
+    @staticmethod
+    def forward(ctx, h, t, g):
+        require_cuda(h, t, g)
+        h, t, g = _c(h), _c(t), _c(g)
+        out = torch.empty_like(h)
+        slot = _amax_pool.take(h.device) if config.conv_operand_format == "fp16" else None
+        check(lib().mflow_glu_residual(ptr(h), ptr(t), ptr(g), ptr(out), ptr(slot), h.numel(), stream()), "mflow_glu_residual")
+        cabi.count_launch()
+        if slot is not None:
+            _publish_amax(out, slot)
+        ctx.save_for_backward(t, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        t, g = ctx.saved_tensors
+        g_out = _c(g_out)
+        g_t, g_g = torch.empty_like(t), torch.empty_like(g)
+        f16 = config.conv_operand_format == "fp16"
+        s_t = _amax_pool.take(t.device) if f16 else None
+        s_g = _amax_pool.take(t.device) if f16 else None
+        check(lib().mflow_glu_residual_backward(ptr(t), ptr(g), ptr(g_out), ptr(g_t), ptr(g_g), ptr(s_t), ptr(s_g), t.numel(), stream()),
+              "mflow_glu_residual_backward")
+        cabi.count_launch()
+        if f16:
+            _publish_amax(g_t, s_t)
+            _publish_amax(g_g, s_g)
+        return g_out, g_t, g_g
+
+
+def glu_residual(h, t, g):
+    """h + t * sigmoid(g) for same-shaped contiguous fp32 CUDA tensors with numel % 4 == 0."""
+    return _GluResidual.apply(h, t, g)
+
+
 # --------------------------------------------------------------------------------------------
 # blocked triangular solve for the wide LU layers (inverse direction of LULinear, lu.py:75-95)
 # --------------------------------------------------------------------------------------------

@@ -211,3 +211,26 @@ def test_blocked_tri_solve_matches_library(cuda_device, n, m, block):
         if mask is not None:
             got, want = got * mask, want * mask
         assert ((got.double() - want).norm() / want.norm()).item() < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 100, 32, 32), (1, 4, 4, 4), (64, 100, 16, 16)])
+def test_glu_residual_matches_torch(cuda_device, shape):
+    """ops.glu_residual = h + t * sigmoid(g), the gated residual of a ResidualBlock with context (nn/resnet.py:36-40:
+    x + glu(cat(t, context_layer(ctx)))), forward and gradients against the ATen expression, with the published maxima."""
+    from manifold_flow.b200 import ops
+
+    torch.manual_seed(7)
+    h, t, g = (torch.randn(*shape, device=cuda_device) * s for s in (2.0, 1.5, 3.0))
+    gy = torch.randn(*shape, device=cuda_device)
+    a = [v.clone().requires_grad_(True) for v in (h, t, g)]
+    out = ops.glu_residual(*a)
+    out.backward(gy)
+    b = [v.clone().requires_grad_(True) for v in (h, t, g)]
+    ref = b[0] + torch.nn.functional.glu(torch.cat((b[1], b[2]), dim=1), dim=1)
+    ref.backward(gy)
+    torch.testing.assert_close(out, ref, rtol=2e-6, atol=2e-6)
+    for u, v in zip(a, b):
+        torch.testing.assert_close(u.grad, v.grad, rtol=5e-6, atol=5e-6)
+    tag = getattr(out, "_mflow_amax", None)
+    assert tag is not None and float(tag[0]) == float(out.detach().abs().max())
