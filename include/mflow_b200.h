@@ -201,6 +201,11 @@ MFLOW_API int mflow_glu_residual(const float* h, const float* t, const float* g,
 MFLOW_API int mflow_glu_residual_backward(const float* t, const float* g, const float* g_out, float* g_t, float* g_g,
                                 float* g_t_amax, float* g_g_amax, int64_t n, void* stream);
 
+/* out = a + b (n floats, n % 4 == 0, 16-byte aligned) with max |out| merged into the optional device scalar out_amax:
+ * the gradient accumulation of a residual block's skip connection (nn/resnet.py:27-40, :91-104 backward), fused with the
+ * operand-scale pass of the convolution that consumes the sum. */
+MFLOW_API int mflow_add_amax(const float* a, const float* b, float* out, float* out_amax, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (b') Vector conditioner: the whole ResidualNet (manifold_flow/nn/resnet.py:9-72) in one launch.
  *   h = W_0 [x | ctx] + b_0;  per block: h += gate * (W_b relu(W_a relu(h) + b_a) + b_b),

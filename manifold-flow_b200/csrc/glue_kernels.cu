@@ -909,3 +909,28 @@ extern "C" MFLOW_API int mflow_glu_residual_backward(const float* t, const float
                                                                                    (float4*)g_t, (float4*)g_g, g_t_amax, g_g_amax, n / 4);
   return check_launch("glu_residual_backward_kernel");
 }
+
+// out = a + b with max |out| published: the gradient accumulation of a residual block's skip connection.  autograd would
+// add the two gradients with an ATen kernel and the consuming convolution would then need an absmax pass over the sum.
+namespace mflow {
+__global__ void __launch_bounds__(256) add_amax_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                                                       float* out_amax, int64_t n4) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = ldg_stream4(a + i), y = ldg_stream4(b + i);
+    const float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    out[i] = o;
+    m = absmax4(m, o);
+  }
+  if (out_amax != nullptr) publish_max(out_amax, m);
+}
+}  // namespace mflow
+
+extern "C" MFLOW_API int mflow_add_amax(const float* a, const float* b, float* out, float* out_amax, int64_t n, void* stream) {
+  MFLOW_REQUIRE(a && b && out && n >= 0, "null pointer");
+  MFLOW_REQUIRE((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "n must be a multiple of 4 and the tensors 16-byte aligned");
+  if (n == 0) return MFLOW_OK;
+  add_amax_kernel<<<glu_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, (float4*)out, out_amax, n / 4);
+  return check_launch("add_amax_kernel");
+}

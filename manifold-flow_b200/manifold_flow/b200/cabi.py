@@ -103,6 +103,7 @@ _SIGNATURES = {
     "mflow_permute_rows": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, c_f32p]),
     "mflow_logtanh_apply": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, i32, f32, c_f32p]),
     "mflow_logtanh_backward": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, i64, i64, i32, f32, c_f32p]),
+    "mflow_add_amax": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p]),
     "mflow_glu_residual": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p]),
     "mflow_glu_residual_backward": (ctypes.c_int, [c_f32p] * 7 + [i64, c_f32p]),
     "mflow_gauss_logprob": (ctypes.c_int, [c_f32p, i64, i64, c_f32p, i64, i64, f32, f32, c_f32p, c_f32p, c_f32p, i64, c_f32p]),

@@ -101,11 +101,14 @@ def residual_net_planes(net, inputs, context):
     ctx_planes = None if context is None else to_planes(context)
     for block in net.blocks:
         lin0, lin1 = block.linear_layers
-        t = lin(h, lin0, relu_in=True)
+        # the block input feeds the branch and the skip connection: their gradients are added (and the sum's absolute
+        # maximum published) by one launch instead of autograd's accumulation plus an absmax pass
+        hb, hs = ops.fork(h) if (h.requires_grad and torch.is_grad_enabled()) else (h, h)
+        t = lin(hb, lin0, relu_in=True)
         if context is None:
-            h = lin(t, lin1, relu_in=True, residual=h)
+            h = lin(t, lin1, relu_in=True, residual=hs)
         else:  # glu(cat(t, gate)) = t * sigmoid(gate)   resnet.py:38-39
-            h = ops.glu_residual(h, lin(t, lin1, relu_in=True), lin(ctx_planes, block.context_layer))
+            h = ops.glu_residual(hs, lin(t, lin1, relu_in=True), lin(ctx_planes, block.context_layer))
     out = lin(h, net.final_layer)
     if _PlanesOut.enabled:
         return out
@@ -127,8 +130,9 @@ def residual_block_conv(x, conv0, conv1, gate_layer, context):
     require_cuda(x)
     with _math_mode():
         if gate_layer is None and _use_tc(x, conv0):
-            t = ops.conv_tc(x, conv0.weight, conv0.bias, relu_in=True)
-            return ops.conv_tc(t, conv1.weight, conv1.bias, residual=x, relu_in=True)
+            xb, xs = ops.fork(x) if (x.requires_grad and torch.is_grad_enabled()) else (x, x)
+            t = ops.conv_tc(xb, conv0.weight, conv0.bias, relu_in=True)
+            return ops.conv_tc(t, conv1.weight, conv1.bias, residual=xs, relu_in=True)
         t = F.conv2d(F.relu(x), conv0.weight, conv0.bias, padding=1)
         t = F.conv2d(F.relu(t), conv1.weight, conv1.bias, padding=1)
         if gate_layer is not None:

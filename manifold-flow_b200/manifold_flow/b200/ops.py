@@ -563,6 +563,41 @@ def residual_net_fused(net, inputs, context):
     return _MlpFused.apply(inputs, context, len(layers), len(net.blocks), *params)
 
 
+class _Fork(torch.autograd.Function):
+    """x -> (x, x): the input of a residual block taken once for the branch and once for the skip connection, so that the
+    two gradients meet HERE and are added by one launch that also publishes max |sum| - autograd's own accumulation is
+    an ATen add, after which the consuming convolution needs an absmax pass over the sum for its operand scale."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g_branch, g_skip):
+        if g_branch is None or g_skip is None:
+            return g_skip if g_branch is None else g_branch
+        a, b = _c(g_branch), _c(g_skip)
+        if a.numel() % 4 or a.dtype != torch.float32 or not a.is_cuda:
+            return a + b
+        out = torch.empty_like(a)
+        slot = _amax_pool.take(a.device) if config.conv_operand_format == "fp16" else None
+        check(lib().mflow_add_amax(ptr(a), ptr(b), ptr(out), ptr(slot), a.numel(), stream()), "mflow_add_amax")
+        cabi.count_launch()
+        if slot is not None:
+            _publish_amax(out, slot)
+        return out
+
+
+def fork(x):
+    """(x, x) as two autograd outputs whose gradients are summed by ``mflow_add_amax``; the views inherit x's amax tag."""
+    a, b = _Fork.apply(x)
+    tag = getattr(x, "_mflow_amax", None)
+    if tag is not None and tag[1] == x._version and tag[2] == x.data_ptr():
+        a._mflow_amax = (tag[0], a._version, a.data_ptr())
+        b._mflow_amax = (tag[0], b._version, b.data_ptr())
+    return a, b
+
+
 class _GluResidual(torch.autograd.Function):
     """out = h + t * sigmoid(g): the gated residual of a ResidualBlock with context (nn/resnet.py:36-40) in one launch each
     way; the absolute maxima of the results ride along for the fp16-split convolutions that consume them."""

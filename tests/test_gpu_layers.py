@@ -234,3 +234,23 @@ def test_glu_residual_matches_torch(cuda_device, shape):
         torch.testing.assert_close(u.grad, v.grad, rtol=5e-6, atol=5e-6)
     tag = getattr(out, "_mflow_amax", None)
     assert tag is not None and float(tag[0]) == float(out.detach().abs().max())
+
+
+@pytest.mark.gpu
+def test_fork_adds_the_two_gradients_and_publishes_their_maximum(cuda_device):
+    """ops.fork(x) = (x, x) for a residual block's branch and skip connection: backward adds the two gradients with
+    mflow_add_amax (same sum as autograd's accumulation) and tags the sum with its absolute maximum."""
+    from manifold_flow.b200 import ops
+
+    torch.manual_seed(2)
+    x = torch.randn(3, 100, 16, 16, device=cuda_device, requires_grad=True)
+    w1, w2 = torch.randn_like(x), torch.randn_like(x)
+    a, b = ops.fork(x)
+    assert a.data_ptr() == x.data_ptr() and torch.equal(a, x) and torch.equal(b, x)
+    (a * w1 + b * w2).sum().backward()
+    torch.testing.assert_close(x.grad, w1 + w2, rtol=0, atol=0)
+    # one branch unused: its gradient is None and the other passes through
+    y = x.detach().clone().requires_grad_(True)
+    c, _ = ops.fork(y)
+    (c * w1).sum().backward()
+    torch.testing.assert_close(y.grad, w1, rtol=0, atol=0)
