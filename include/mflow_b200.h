@@ -265,6 +265,23 @@ MFLOW_API int mflow_conv2d_f16x3(const mflow_conv_desc* desc, const float* x, co
                        const float* w_unscale, const float* in_amax, const float* bias, const float* residual,
                        const float* gate, float* y, float* out_amax, void* stream);
 
+/* The conditioner's FINAL 1x1 convolution of an image coupling layer with the coupling layer's spline in its epilogue
+ * (manifold_flow/transforms/coupling.py:108-110 + :264-279 + splines/rational_quadratic.py:16-168):
+ * C_out = 32 C_t, so the 32 spline parameters of a transformed channel are one 32-column chunk of the pixel's
+ * accumulator row; the epilogue evaluates the spline on them and writes y and partial log-dets - the
+ * [B, C_t * 32, H, W] parameter tensor (128 of the 136 bytes the spline moves per element) never exists.
+ * Evaluation / sampling only (no backward: the training path keeps the parameters for mflow_rqs_backward).
+ *   desc        : the 1x1 convolution (x = the conditioner's last hidden activation [B, c_in, H, W])
+ *   sd          : the spline as for mflow_rqs_apply in the planes layout (num_bins == 11, n_chan == c_out / 32,
+ *                 n_inner == H * W; the p_* fields are unused); x_full / y_full as x / y there (shifted to the first
+ *                 transformed channel, identity channels copied through)
+ *   lad_sample  : [B] per-sample log-dets
+ *   workspace   : mflow_conv2d_rqs_workspace_bytes(desc) bytes of device scratch (the partial log-dets) */
+MFLOW_API int64_t mflow_conv2d_rqs_workspace_bytes(const mflow_conv_desc* desc);
+MFLOW_API int mflow_conv2d_rqs_f16x3(const mflow_conv_desc* desc, const float* x, const void* w_hi, const void* w_lo,
+                           const float* w_unscale, const float* in_amax, const float* bias, const mflow_rqs_desc* sd,
+                           const float* x_full, float* y_full, float* lad_sample, void* workspace, void* stream);
+
 /* max |x| over n floats (x 16-byte aligned) merged into *out, which the caller zero-initialises: the operand
  * scale of the fp16-split kernels for tensors whose producer did not publish it. */
 MFLOW_API int mflow_absmax(const float* x, int64_t n, float* out, void* stream);

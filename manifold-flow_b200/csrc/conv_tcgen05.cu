@@ -38,6 +38,7 @@
 #include <stdlib.h>
 
 #include "mflow_common.cuh"
+#include "rqs_math.cuh"
 #include "tc_ptx.cuh"
 #include "tma_encode.cuh"
 
@@ -84,6 +85,17 @@ struct ConvArgs {
   const float* in_amax;   // device scalar: absolute maximum of x (null = no scaling: the caller vouches for the range)
   const float* w_unscale; // [n_pad] 2^-s_n undoing the per-output-channel weight scale
   float* out_amax;        // device scalar (zero-initialised by the caller) receiving max |y| of this launch, or null
+  // Spline epilogue (template parameter SPL != 0): this launch is the conditioner's FINAL 1x1 convolution of an image
+  // coupling layer (C_out = C_t * 32: the P = 32 spline parameters of transformed channel c are the accumulator columns
+  // 32 c .. 32 c + 31 of the pixel's TMEM lane) and the coupling layer's spline is evaluated right there: the
+  // [B, C_t * 32, H, W] parameter tensor never exists (coupling.py:108-110; evaluation only).
+  const float* sp_x;      // activation tensor of the coupling layer, pointing at its first transformed channel
+  float* sp_y;            // output tensor, same indexing
+  float* sp_lad;          // [B][sp_slots] partial log-dets: one per 16 pixels and transformed channel
+  int64_t sp_so, sp_sc;   // sample / transformed-channel strides of x and y (floats)
+  int64_t sp_id_off, sp_id_sc;   // identity channels (copied through), relative to sp_x
+  int sp_n_id, sp_slots;
+  RqsConsts sp_c;
 #ifdef MFLOW_CONV_ABLATE
   int ablate;             // dev-only timing experiments (wrong results): 1 no B_lo product, 2 no gather loads, 4 MMA N = 64, 16 no TMEM stores
 #endif
@@ -118,7 +130,7 @@ struct Ring {
 
 // CS: compile-time number of floats between two channels of the raw box (box_w * box_h; 0 = read it from the
 // arguments): the gather's 32 shared-memory loads then use immediate offsets instead of one address multiply each.
-template <bool F16, int CS>
+template <bool F16, int CS, int SPL = 0>   // SPL: 0 plain convolution, 1 / 2 spline epilogue forward / inverse
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_whi8,
@@ -401,6 +413,46 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       fac_l[q] = F16 ? inv_sa * __ldg(a.w_unscale + co) : 1.f;
       bias_l[q] = (a.bias != nullptr && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
     }
+    if constexpr (SPL != 0) {
+      // ===== spline epilogue: thread = pixel, one 32-column chunk = the 32 parameters of one transformed channel =====
+      const int b = b0 + pbl;
+      const bool valid = b < a.B;
+      const int pix = (h0 + phl) * a.W + pw;                       // pixel within the image plane
+      const int64_t base = (int64_t)b * a.sp_so + pix;
+      if (blockIdx.y == 0 && valid)                                 // identity channels pass through (coupling.py:116-118)
+        for (int k = half; k < a.sp_n_id; k += 2) {
+          const int64_t off = base + a.sp_id_off + k * a.sp_id_sc;
+          a.sp_y[off] = __ldg(a.sp_x + off);
+        }
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < kTileN; c0 += 64) {
+        if (n0 + c0 >= a.Cout) break;
+        float v[32];
+        tmem_ld_32x32(t_lane + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float bj = __shfl_sync(0xffffffffu, c0 >= 64 ? bias_l[1] : bias_l[0], j);
+          v[j] = F16 ? fmaf(v[j], __shfl_sync(0xffffffffu, c0 >= 64 ? fac_l[1] : fac_l[0], j), bj) : v[j] + bj;
+        }
+        const int ch = (n0 + c0) >> 5;
+        float lad = 0.f;
+        if (valid) {
+          const int64_t off = base + ch * a.sp_sc;
+          float out;
+          int bin;
+          rqs_eval<11, SPL == 2>(__ldg(a.sp_x + off), v, a.sp_c, out, lad, bin);
+          a.sp_y[off] = out;
+        }
+        // 16 consecutive pixels belong to one image for every map size: one partial per half warp, summed in a fixed order
+        lad += __shfl_xor_sync(0xffffffffu, lad, 1);
+        lad += __shfl_xor_sync(0xffffffffu, lad, 2);
+        lad += __shfl_xor_sync(0xffffffffu, lad, 4);
+        lad += __shfl_xor_sync(0xffffffffu, lad, 8);
+        if ((lane & 15) == 0 && valid) a.sp_lad[(int64_t)b * a.sp_slots + (pix >> 4) * (a.Cout >> 5) + ch] = lad;
+      }
+    } else {
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     MFLOW_TL(3, warp == 2 && lane == 0);
@@ -446,6 +498,7 @@ conv_split3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     if (issuer) tma_store_wait_read<0>();  // shared memory must stay valid until the stores have read it
     MFLOW_TL(4, warp == 2 && lane == 0);
+    }   // SPL == 0
   }
   tc_fence_before();
   __syncthreads();
@@ -483,8 +536,9 @@ extern "C" MFLOW_API int mflow_debug_conv_steps(long long* out) {
 template <bool F16>
 static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_hi, const void* w_lo, const float* w_unscale,
                        const float* in_amax, const float* bias, const float* residual, const float* gate, float* y, float* out_amax,
-                       void* stream) {
-  MFLOW_REQUIRE(d && x && w_hi && w_lo && y, "null pointer");
+                       void* stream, const mflow_rqs_desc* sd = nullptr, const float* sp_x = nullptr, float* sp_y = nullptr,
+                       float* sp_lad = nullptr) {
+  MFLOW_REQUIRE(d && x && w_hi && w_lo && (y || sd), "null pointer");
   MFLOW_REQUIRE(!F16 || w_unscale, "the fp16 path needs the per-channel weight unscale vector");
   MFLOW_REQUIRE(!(residual && gate), "residual and gate cannot be combined in one call");
   MFLOW_REQUIRE(d->kernel == 3 || d->kernel == 1, "kernel size must be 1 or 3");
@@ -500,6 +554,26 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   ConvArgs a{};
   a.y = y; a.bias = bias; a.residual = residual; a.gate = gate;
   a.in_amax = in_amax; a.w_unscale = w_unscale; a.out_amax = out_amax;
+  if (sd != nullptr) {   // spline epilogue: the final 1x1 convolution of an image coupling layer, K = 11 (P = 32)
+    MFLOW_REQUIRE(F16 && d->kernel == 1 && d->c_out % 32 == 0 && sd->num_bins == 11 && !residual && !gate && !out_amax && sp_x && sp_y && sp_lad,
+                  "spline epilogue: fp16 format, 1x1 convolution with C_out = 32 C_t, 11 bins");
+    MFLOW_REQUIRE(sd->n_chan * 32 == d->c_out && sd->n_outer == d->batch && sd->n_inner == d->height * d->width && sd->x_so == sd->y_so &&
+                      sd->x_sc == sd->y_sc && sd->tail_bound > 0.f && sd->wh_divisor > 0.f,
+                  "spline epilogue: descriptor does not match the convolution");
+    MFLOW_REQUIRE((double)sd->min_bin_width * 11 <= 1.0, "Minimal bin width too large for the number of bins");
+    MFLOW_REQUIRE((double)sd->min_bin_height * 11 <= 1.0, "Minimal bin height too large for the number of bins");
+    a.sp_x = sp_x; a.sp_y = sp_y; a.sp_lad = sp_lad;
+    a.sp_so = sd->x_so; a.sp_sc = sd->x_sc; a.sp_id_off = sd->id_off; a.sp_id_sc = sd->id_sc; a.sp_n_id = (int)sd->n_id_chan;
+    a.sp_slots = (int)(d->height * d->width / 16 * (d->c_out / 32));
+    RqsConsts& c = a.sp_c;
+    const double T = (double)sd->tail_bound;
+    c.tail = (float)T; c.lo = (float)(-T); c.span = (float)(T - (-T));
+    c.min_w = sd->min_bin_width; c.min_h = sd->min_bin_height; c.min_d = sd->min_derivative;
+    c.cfac_w = (float)(1.0 - (double)sd->min_bin_width * 11);
+    c.cfac_h = (float)(1.0 - (double)sd->min_bin_height * 11);
+    c.edge = (float)log(exp(1.0 - (double)sd->min_derivative) - 1.0);
+    c.divisor = sd->wh_divisor; c.rcp_divisor = 1.0f / sd->wh_divisor; c.use_divisor = sd->wh_divisor != 1.0f;
+  }
 #ifdef MFLOW_CONV_ABLATE
   { const char* e = getenv("MFLOW_CONV_ABLATE"); a.ablate = e ? atoi(e) : 0; }
 #endif
@@ -573,10 +647,10 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
     cuuint64_t dims[4] = {d0, d1, (cuuint64_t)a.Cout, (cuuint64_t)B};
     cuuint64_t str[3] = {s1, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
     cuuint32_t box[4] = {b0x, b1x, 32u, (cuuint32_t)a.imgs_per_tile};
-    if (!encode(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
+    if (sd == nullptr && !encode(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MFLOW_E_BADARG;
   }
   {  // aux (residual / gate), shaped like y: box {W, rows, 32 channels, images}
-    const float* auxp = residual ? residual : (gate ? gate : y);
+    const float* auxp = residual ? residual : (gate ? gate : (y ? y : x));
     cuuint64_t dims[4] = {d0, d1, (cuuint64_t)a.Cout, (cuuint64_t)B};
     cuuint64_t str[3] = {s1, (cuuint64_t)H * W * 4, (cuuint64_t)a.Cout * H * W * 4};
     cuuint32_t box[4] = {b0x, b1x, 32u, (cuuint32_t)a.imgs_per_tile};
@@ -606,21 +680,30 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
   // the opt-in shared-memory limit is a per-device function attribute
   int dev = 0;
   cudaGetDevice(&dev);
-#define MFLOW_CONV_LAUNCH(CS_)                                                                                             \
+#define MFLOW_CONV_LAUNCH_(CS_, SPL_)                                                                                      \
   do {                                                                                                                     \
     static bool attr_set[64] = {};   /* the opt-in shared-memory limit is a per-device function attribute */               \
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {                                                                          \
-      cudaFuncSetAttribute(conv_split3_kernel<F16, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_cta_budget); \
+      cudaFuncSetAttribute(conv_split3_kernel<F16, CS_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_cta_budget); \
       attr_set[dev] = true;                                                                                                \
     }                                                                                                                      \
-    conv_split3_kernel<F16, CS_><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a); \
+    conv_split3_kernel<F16, CS_, SPL_><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(mx, mhi, mlo, mhi8, mlo8, maux, my, a); \
   } while (0)
+#define MFLOW_CONV_LAUNCH(CS_) MFLOW_CONV_LAUNCH_(CS_, 0)
   const int cs = a.flat ? 0 : a.box_w * a.box_h;
+  if (sd != nullptr) {   // spline epilogue: 1x1 boxes of the 32x32 / 16x16 levels (128 floats per channel) or flat boxes
+    if (!F16) return MFLOW_E_BADARG;
+    my = mx;             // never used: the epilogue writes y itself
+    if (cs == 128) { if (sd->inverse) MFLOW_CONV_LAUNCH_(128, 2); else MFLOW_CONV_LAUNCH_(128, 1); }
+    else { if (sd->inverse) MFLOW_CONV_LAUNCH_(0, 2); else MFLOW_CONV_LAUNCH_(0, 1); }
+    return check_launch("conv_split3_kernel<fp16, spline epilogue>");
+  }
   if (F16 && cs == 240) MFLOW_CONV_LAUNCH(240);        // 3x3 on 32x32 and 16x16 maps
   else if (F16 && cs == 160) MFLOW_CONV_LAUNCH(160);   // 3x3 on 8x8 maps
   else if (F16 && cs == 128) MFLOW_CONV_LAUNCH(128);   // 1x1
   else MFLOW_CONV_LAUNCH(0);
 #undef MFLOW_CONV_LAUNCH
+#undef MFLOW_CONV_LAUNCH_
   return check_launch(F16 ? "conv_split3_kernel<fp16>" : "conv_split3_kernel<tf32>");
 }
 
@@ -634,6 +717,38 @@ extern "C" MFLOW_API int mflow_conv2d_f16x3(const mflow_conv_desc* d, const floa
                                             const float* w_unscale, const float* in_amax, const float* bias, const float* residual,
                                             const float* gate, float* y, float* out_amax, void* stream) {
   return launch_conv<true>(d, x, w_hi, w_lo, w_unscale, in_amax, bias, residual, gate, y, out_amax, stream);
+}
+
+namespace mflow {
+// lad_sample[b] = sum of the sample's partial log-dets in index order (one warp per sample: strided sums, shuffle tree)
+__global__ void __launch_bounds__(256) rqs_lad_reduce_kernel(const float* __restrict__ partial, int slots, float* __restrict__ lad, int B) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int i = lane; i < slots; i += 32) s += partial[(int64_t)b * slots + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) lad[b] = s;
+}
+}  // namespace mflow
+
+extern "C" MFLOW_API int64_t mflow_conv2d_rqs_workspace_bytes(const mflow_conv_desc* d) {
+  if (!d || d->batch < 1) return 0;
+  return d->batch * (d->height * d->width / 16) * (d->c_out / 32) * (int64_t)sizeof(float);
+}
+
+extern "C" MFLOW_API int mflow_conv2d_rqs_f16x3(const mflow_conv_desc* d, const float* x, const void* w_hi, const void* w_lo,
+                                                const float* w_unscale, const float* in_amax, const float* bias,
+                                                const mflow_rqs_desc* sd, const float* x_full, float* y_full, float* lad_sample,
+                                                void* workspace, void* stream) {
+  MFLOW_REQUIRE(d && sd && x_full && y_full && lad_sample && workspace, "null pointer");
+  if (d->batch == 0) return MFLOW_OK;
+  if (int rc = launch_conv<true>(d, x, w_hi, w_lo, w_unscale, in_amax, bias, nullptr, nullptr, nullptr, nullptr, stream, sd, x_full, y_full,
+                                 (float*)workspace))
+    return rc;
+  const int slots = (int)(d->height * d->width / 16 * (d->c_out / 32));
+  rqs_lad_reduce_kernel<<<(unsigned)((d->batch + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, slots, lad_sample, (int)d->batch);
+  return check_launch("rqs_lad_reduce_kernel");
 }
 
 // max |x| over n floats -> *out (zero-initialised by the caller; bits compared as unsigned): the operand scale of the

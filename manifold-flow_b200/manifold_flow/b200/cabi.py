@@ -92,6 +92,8 @@ _SIGNATURES = {
     "mflow_conv2d_wgrad_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 8),
     "mflow_absmax": (ctypes.c_int, [c_f32p, i64, c_f32p, c_f32p]),
     "mflow_conv2d_wgrad_workspace_bytes": (i64, [ctypes.POINTER(ConvDesc)]),
+    "mflow_conv2d_rqs_workspace_bytes": (i64, [ctypes.POINTER(ConvDesc)]),
+    "mflow_conv2d_rqs_f16x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 6 + [ctypes.POINTER(RqsDesc)] + [c_f32p] * 5),
     "mflow_conv2d_wgrad_tf32x3": (ctypes.c_int, [ctypes.POINTER(ConvDesc)] + [c_f32p] * 6),
     "mflow_chanmix_apply": (ctypes.c_int, [ctypes.POINTER(MixDesc)] + [c_f32p] * 5),
     "mflow_chanmix_wgrad_workspace_bytes": (i64, [ctypes.POINTER(MixDesc)]),

@@ -23,6 +23,9 @@ class _Config:
     # below that row count: the whole ResidualNet as one fused launch (mflow_mlp_forward / _backward); False = one cuBLAS
     # GEMM and a few ATen launches per layer
     fuse_vector_conditioner = os.environ.get("MFLOW_FUSE_MLP", "1") != "0"
+    # evaluation (no-grad) passes of the image couplings: the spline runs in the epilogue of the conditioner's final 1x1
+    # convolution and the parameter tensor is never written
+    fuse_spline_epilogue = os.environ.get("MFLOW_FUSE_SPLINE", "1") != "0"
     # build the dense L / U / W / W^-1 matrices of all same-width LU layers of a model in one batched pass
     batch_lu_builds = os.environ.get("MFLOW_BATCH_LU", "1") != "0"
     # fuse ActNorm + 1x1 convolution (+ permutation + LU) into one channel-mix launch

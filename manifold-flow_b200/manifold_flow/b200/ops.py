@@ -76,7 +76,7 @@ def _rqs_desc(x, params, geom, num_bins, tail_bound, min_w, min_h, min_d, diviso
     d.tail_bound, d.min_bin_width, d.min_bin_height, d.min_derivative = tail_bound, min_w, min_h, min_d
     d.wh_divisor = divisor
     d.n_id_chan, d.id_off, d.id_sc = geom.n_identity, geom.i_offset * inner, geom.i_step * inner
-    if x.dim() == 2 and params.dim() == 4:   # rows x planes: unshifted row pointers, the kernel stages whole rows
+    if params is not None and x.dim() == 2 and params.dim() == 4:   # rows x planes: unshifted row pointers, the kernel stages whole rows
         d.p_hw, d.t_off = params.shape[2] * params.shape[3], geom.t_offset
         return d, 0
     d.p_hw = d.t_off = 0
@@ -401,6 +401,41 @@ def _conv_tc_launch(x, split, c_out, kernel, bias, residual, gate, relu_in, x_am
     if f16:
         _publish_amax(y, out_amax)
     return y
+
+
+def conv_rqs_supported(hidden, weight, x_full, num_bins):
+    """Can the final 1x1 convolution of a conditioner run with the coupling layer's spline in its epilogue?"""
+    return (config.fuse_spline_epilogue and config.conv_tensor_cores and config.conditioner_math == "fp32"
+            and config.conv_operand_format == "fp16" and num_bins == 11 and weight.shape[2] == 1 and weight.shape[0] % 32 == 0
+            and conv_tc_supported(hidden, weight) and x_full.dim() == 4 and not torch.is_grad_enabled())
+
+
+def conv_rqs(hidden, weight, bias, x_full, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse):
+    """(y_full, logabsdet[B]) of an image coupling layer whose conditioner ends in ``conv2d(hidden, weight, bias)`` (1x1):
+    one launch computes the convolution and evaluates the spline on its accumulator rows (no autograd: evaluation only)."""
+    require_cuda(hidden, weight, bias, x_full)
+    hidden, x_full = _c(hidden), _c(x_full)
+    b, c_in, h, w = hidden.shape
+    c_out = weight.shape[0]
+    split = _weight_cache.get(weight, False, None, "fp16")
+    hi, lo, unscale, n_pad, k_pad = split
+    d = ConvDesc(batch=b, c_in=c_in, c_out=c_out, height=h, width=w, kernel=1, relu_in=0, relu_out=0, n_pad=n_pad, k_pad=k_pad)
+    sd, off = _rqs_desc(x_full, None, geom, num_bins, tail_bound, min_w, min_h, min_d, divisor, inverse)
+    sd.id_off -= off
+    y = torch.empty_like(x_full)
+    lad = torch.empty(b, dtype=torch.float32, device=x_full.device)
+    ws = cabi.workspace("conv_rqs", lib().mflow_conv2d_rqs_workspace_bytes(ctypes.byref(d)), x_full.device)
+    xo = ctypes.c_void_p(x_full.data_ptr() + 4 * off)
+    yo = ctypes.c_void_p(y.data_ptr() + 4 * off)
+    tok = None
+    if cabi.kernel_timer:
+        tok = cabi.kernel_timer.begin(f"conv1x1+rqs[{b}x{c_in}->{c_out}x{h}x{w}]", 2 * b * h * w * c_in * c_out)
+    check(lib().mflow_conv2d_rqs_f16x3(ctypes.byref(d), ptr(hidden), ptr(hi), ptr(lo), ptr(unscale), ptr(tensor_amax(hidden)), ptr(bias),
+                                       ctypes.byref(sd), xo, yo, ptr(lad), ptr(ws), stream()), "mflow_conv2d_rqs_f16x3")
+    if tok:
+        cabi.kernel_timer.end(tok)
+    cabi.count_launch(2)
+    return y, lad
 
 
 def conv_wgrad_supported(x, c_out, kernel):

@@ -105,6 +105,11 @@ class ConvResidualNet(nn.Module):
         self.final_layer = nn.Conv2d(hidden_channels, out_channels, kernel_size=1, padding=0)
 
     def forward(self, inputs, context=None):
+        return K.conv(self.hidden(inputs, context), self.final_layer)
+
+    def hidden(self, inputs, context=None):
+        """Everything but the final 1x1 convolution (:130-140).  The coupling layer calls this in evaluation passes and
+        runs the final layer with its spline in the epilogue (``ops.conv_rqs``)."""
         if context is not None and context.dim() < inputs.dim():  # vector context -> constant image planes (:130-133)
             if context.dim() != 2 or inputs.dim() != 4:
                 raise ValueError("context must be [B, F] for [B, C, H, W] inputs")
@@ -112,4 +117,4 @@ class ConvResidualNet(nn.Module):
         temps = K.conv(inputs if context is None else torch.cat((inputs, context), dim=1), self.initial_layer)
         for block in self.blocks:
             temps = block(temps, context)
-        return K.conv(temps, self.final_layer)
+        return temps

@@ -113,6 +113,13 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
                 with conditioner.planes_output():
                     params = self.transform_net(self._identity_view(inputs), context)
             else:
+                net = self.transform_net
+                final = getattr(net, "final_layer", None)
+                if (hasattr(net, "hidden") and isinstance(final, torch.nn.Conv2d)
+                        and ops.conv_rqs_supported(inputs, final.weight, inputs, self.num_bins)):
+                    # evaluation pass of an image coupling: the spline runs in the epilogue of the final 1x1 convolution
+                    hidden = net.hidden(self._identity_view(inputs), context)
+                    return ops.conv_rqs(hidden, final.weight, final.bias, inputs, self._geometry, *args)
                 params = self.transform_net(self._identity_view(inputs), context)
             return ops.rqs_coupling(inputs, params, self._geometry, *args)
         params = self.transform_net(self._identity_view(inputs), context)

@@ -254,3 +254,45 @@ def test_fork_adds_the_two_gradients_and_publishes_their_maximum(cuda_device):
     c, _ = ops.fork(y)
     (c * w1).sum().backward()
     torch.testing.assert_close(y.grad, w1, rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,c,hw", [(5, 12, 32), (3, 24, 16), (7, 48, 8), (9, 96, 4), (256, 96, 4)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_in_conv_epilogue_equals_two_launches(cuda_device, batch, c, hw, inverse):
+    """Evaluation passes of an image coupling layer run the spline in the epilogue of the conditioner's final 1x1
+    convolution (ops.conv_rqs; coupling.py:108-110): same outputs and log-dets as the convolution
+    followed by the spline launch (the training path), for every level of the 64x64x3 models, both directions."""
+    from manifold_flow import nn as nn_
+    from manifold_flow import transforms
+    from manifold_flow.b200 import config, ops
+    from manifold_flow.utils import various
+
+    calls = []
+    real = ops.conv_rqs
+    torch.manual_seed(batch + c + hw)
+    mask = various.create_mid_split_binary_mask(c) if c == 96 else various.create_alternating_binary_mask(c, even=(hw == 16))
+    layer = transforms.PiecewiseRationalQuadraticCouplingTransform(
+        mask=mask,
+        transform_net_create_fn=lambda i, o: nn_.ConvResidualNet(in_channels=i, out_channels=o, hidden_channels=100, num_blocks=2),
+        tails="linear", tail_bound=10.0, num_bins=11, apply_unconditional_transform=False).to(cuda_device)
+    with torch.no_grad():   # the final layer is zero-initialised-ish (1e-3): make the spline non-trivial
+        layer.transform_net.final_layer.weight.mul_(100.0)
+        layer.transform_net.final_layer.bias.normal_(0.0, 2.0)
+    x = torch.randn(batch, c, hw, hw, device=cuda_device) * 4.0
+    results = []
+    ops.conv_rqs = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    try:
+        for fused in (True, False):
+            config.fuse_spline_epilogue = fused
+            with torch.no_grad():
+                y, lad = layer._apply_transform(x, None, inverse)
+            results.append((y, lad, len(calls)))
+    finally:
+        config.fuse_spline_epilogue = True
+        ops.conv_rqs = real
+    (y1, l1, n1), (y0, l0, n0) = results
+    assert n1 == 1 and n0 == 1                                 # the first pass really took the fused path, the second did not
+    torch.testing.assert_close(y1, y0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(l1, l0, rtol=1e-5, atol=1e-4, equal_nan=True)
+    assert float((y1 != y0).float().mean()) < 1e-3             # the arithmetic is the same functions on the same values
