@@ -692,11 +692,14 @@ static int launch_conv(const mflow_conv_desc* d, const float* x, const void* w_h
 #define MFLOW_CONV_LAUNCH(CS_) MFLOW_CONV_LAUNCH_(CS_, 0)
   const int cs = a.flat ? 0 : a.box_w * a.box_h;
   if (sd != nullptr) {   // spline epilogue: 1x1 boxes of the 32x32 / 16x16 levels (128 floats per channel) or flat boxes
-    if (!F16) return MFLOW_E_BADARG;
-    my = mx;             // never used: the epilogue writes y itself
-    if (cs == 128) { if (sd->inverse) MFLOW_CONV_LAUNCH_(128, 2); else MFLOW_CONV_LAUNCH_(128, 1); }
-    else { if (sd->inverse) MFLOW_CONV_LAUNCH_(0, 2); else MFLOW_CONV_LAUNCH_(0, 1); }
-    return check_launch("conv_split3_kernel<fp16, spline epilogue>");
+    if constexpr (F16) {
+      my = mx;           // never used: the epilogue writes y itself
+      if (cs == 128) { if (sd->inverse) MFLOW_CONV_LAUNCH_(128, 2); else MFLOW_CONV_LAUNCH_(128, 1); }
+      else { if (sd->inverse) MFLOW_CONV_LAUNCH_(0, 2); else MFLOW_CONV_LAUNCH_(0, 1); }
+      return check_launch("conv_split3_kernel<fp16, spline epilogue>");
+    } else {
+      return MFLOW_E_BADARG;   // (unreachable: checked above)
+    }
   }
   if (F16 && cs == 240) MFLOW_CONV_LAUNCH(240);        // 3x3 on 32x32 and 16x16 maps
   else if (F16 && cs == 160) MFLOW_CONV_LAUNCH(160);   // 3x3 on 8x8 maps
